@@ -1,0 +1,150 @@
+/*
+ * ndppgpu.h -- C-ABI of libndppgpu.so, the B200 (sm_100a) scattering-moment integrator for NDPP.
+ *
+ * The reference (ndpp/ndpp, Fortran) has no plugin or FFI interface; the boundary is the Fortran
+ * procedure seam inside calc_scatt / calc_scattsab (src/scatt.F90:33,543).  Each entry point
+ * below replaces one reference routine; the Fortran driver, ndpp.xml handling, ACE parsing,
+ * E_in grid construction, tolerance/thinning and output stay in the reference and call these
+ * through ISO_C_BINDING (the interface module is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; ndppgpu_last_error() gives the
+ *     text (the Fortran wrapper passes it to fatal_error, src/error.F90:79).  No exceptions
+ *     cross the ABI.
+ *   - the caller owns every host array; the library copies during the call and keeps nothing.
+ *   - index-valued arguments (threshold, locators inside the raw ACE blocks) are 1-based /
+ *     ACE-relative exactly as the reference stores them (src/ace_header.F90, src/ace.F90).
+ *   - moment arrays are Fortran `mat(L, G, NE)` column-major == C `mat[iE][g][l]`, l contiguous,
+ *     L = order+1 for Legendre output (src/scattdata_header.F90:114-118).
+ *   - there is no CPU fallback: without a CUDA device every call fails with an error.
+ */
+#ifndef NDPPGPU_H
+#define NDPPGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDPPGPU_ABI_VERSION 1
+
+/* run-time integration parameters: src/global.F90:28-59, defaults src/constants.F90:69-100 */
+typedef struct {
+    int scatt_type;        /* SCATT_TYPE_LEGENDRE = 0 (TABULAR = 1 is unimplemented in the reference) */
+    int order;             /* scatt_order (L-1 for Legendre) */
+    int mu_bins;           /* M, points of the uniform mu grid */
+    int nuscatter;         /* also build nuinel_mat */
+    int ne_per_grp;        /* NE_PER_GRP */
+    int adaptive_mu_its;   /* ADAPTIVE_MU_ITS */
+    int adaptive_eout_its; /* ADAPTIVE_EOUT_ITS */
+    int reserved;
+    double sab_threshold;     /* SAB_THRESHOLD */
+    double brent_mu_thresh;   /* BRENT_MU_THRESH */
+    double adaptive_mu_tol;   /* ADAPTIVE_MU_TOL */
+    double adaptive_eout_tol; /* ADAPTIVE_EOUT_TOL */
+} ndppgpu_params;
+
+/* counters of the work done since the last reset (ndppgpu_stats) */
+typedef struct {
+    double kernel_ms;        /* CUDA-event time of all kernels launched by the integrator calls */
+    double h2d_bytes;        /* host->device bytes copied by the calls */
+    double d2h_bytes;        /* device->host bytes copied by the calls */
+    long long launches;      /* kernels launched */
+    long long moment_evals;  /* output elements (E_in, g, l) produced */
+    long long file4_calls;   /* integrate_file4_cm_leg evaluations (E_in x reaction x table row) */
+    long long file6_cm_points; /* inner (group, E_out, mu) points of integrate_file6_cm_leg */
+    long long file6_lab_calls;
+    long long freegas_tasks; /* adaptive (E_in, row, g, l) free-gas integrations */
+    long long sab_columns;
+    double file6_cm_ms;      /* CUDA-event time of the dominant kernel (k_file6_cm) alone */
+    long long file6_cm_launches;
+    double reserved[6];
+} ndppgpu_stats_t;
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* One context per process and device (the reference's MPI rank / OpenMP team, src/ndpp.F90:934).
+ * device < 0 selects the current CUDA device. */
+int ndppgpu_init(int device, void **ctx);
+int ndppgpu_finalize(void *ctx);
+int ndppgpu_last_error(void *ctx /* may be NULL */, char *buf, int len);
+int ndppgpu_stats(void *ctx, ndppgpu_stats_t *out, int reset);
+int ndppgpu_abi_version(void);
+/* the CUDA stream all work of this context is issued on (as cudaStream_t) */
+void *ndppgpu_stream(void *ctx);
+
+/* ---- continuous-energy nuclide: replaces the body of calc_scatt between create_Ein_grid and the
+ *      output (src/scatt.F90:84-155) ------------------------------------------------------------ */
+/* type(Nuclide) scalars + energy grid + elastic xs (src/ace_header.F90:94-112), the group
+ * structure and the integration parameters. */
+int ndppgpu_nuclide_create(void *ctx, double awr, double kT, double freegas_cutoff, int n_grid,
+                           const double *energy, const double *elastic_xs, const double *e_bins,
+                           int n_bins /* G+1 */, const ndppgpu_params *params, void **nuc);
+
+/* One call per ScattData slot, in the order calc_scatt fills rxn_data(:) (src/scatt.F90:88-105):
+ * each reaction once, then once more per nested energy distribution (edist%next).  Calls that
+ * share `rxn_index` describe the same reaction; the reaction-level arguments (MT .. adist_*) are
+ * taken from the first of them.  Performs scatt_init (src/scattdata_header.F90:78-271), i.e. the
+ * MT / law filter, the isotropic-adist synthesis and the table allocation.
+ *   yield_tab1 / p_valid_tab1: TAB1 flattened as [NR, NBT(NR), INT(NR), NP, x(NP), y(NP)]
+ *                              (src/interpolation.F90:24-60); NULL,0 when absent.
+ *   adist_*:  DistAngle (src/ace_header.F90:14-24); edist_data: DistEnergy%data (raw DLW block). */
+int ndppgpu_nuclide_add_reaction(void *nuc, int rxn_index, int MT, double Q_value, int threshold,
+                                 int scatter_in_cm, int has_angle_dist, int has_energy_dist, int law,
+                                 int multiplicity, const double *yield_tab1, int n_yield,
+                                 const double *sigma, int n_sigma, const double *p_valid_tab1,
+                                 int n_pvalid, const double *adist_energy, const int *adist_type,
+                                 const int *adist_loc, int n_adist_e, const double *adist_data,
+                                 int n_adist_data, const double *edist_data, int n_edist_data);
+
+/* scatt_convert_distro for every slot (src/scattdata_header.F90:325-382): ACE -> uniform-mu tables,
+ * computed on the device. */
+int ndppgpu_convert_distro(void *nuc);
+
+/* calc_elastic_grid (src/scatt.F90:603-675): el_mat[NE][G][L]. */
+int ndppgpu_elastic(void *nuc, const double *Ein, int NE, double *el_mat);
+/* calc_inelastic_grid (src/scatt.F90:682-778): inel_mat[NE][G][L]; nuinel_mat may be NULL. */
+int ndppgpu_inelastic(void *nuc, const double *Ein, int NE, double *inel_mat, double *nuinel_mat);
+/* Same, with E_in and the result left in device memory (pointers are device pointers of this
+ * context's device).  Used to shard E_in ranges over GPUs and gather with NCCL. */
+int ndppgpu_elastic_dev(void *nuc, const double *d_Ein, int NE, double *d_el_mat);
+int ndppgpu_inelastic_dev(void *nuc, const double *d_Ein, int NE, double *d_inel_mat, double *d_nuinel_mat);
+
+/* introspection used by the parity tests */
+int ndppgpu_nuclide_n_slots(void *nuc);
+/* info[8] = is_init, NE, law, has_adist, has_edist, order(L), groups, MT */
+int ndppgpu_nuclide_slot_info(void *nuc, int slot, int *info);
+int ndppgpu_nuclide_slot_row_np(void *nuc, int slot, int iE /* 1-based */);
+/* row iE of the converted tables: distro[NP][M] (== Fortran data(M,NP)), Eouts/pdf/cdf[NP] */
+int ndppgpu_nuclide_get_table(void *nuc, int slot, int iE, double *distro, double *Eouts, double *pdf,
+                              double *cdf, int *INTT);
+/* ScattData%clear for all slots (src/scatt.F90:153-155) */
+int ndppgpu_nuclide_free(void *nuc);
+
+/* ---- thermal S(a,b): replaces integrate_sab_el/_inel + combine_sab_grid in calc_scattsab
+ *      (src/scatt.F90:573-591; src/sab.F90:21-454) ---------------------------------------------- */
+/* type(SAlphaBeta) (src/ace_header.F90:201-235), flattened with the Fortran column-major order:
+ *   inelastic_e_out(NEo,NEi) -> [iEin][iEout];  inelastic_mu(n_mu,NEo,NEi) -> [iEin][iEout][imu]
+ *   continuous mode (secondary_mode = 2): cont_n_e_out[NEi] and the rows of e_out / e_out_pdf /
+ *   mu(n_mu, NEo_i) concatenated;  elastic_mu(n_mu,NEe) -> [iEin][imu]. */
+int ndppgpu_sab_create(void *ctx, double awr, double kT, double threshold_inelastic, double threshold_elastic,
+                       int n_inelastic_e_in, int n_inelastic_e_out, int n_inelastic_mu, int secondary_mode,
+                       const double *inelastic_e_in, const double *inelastic_sigma, const double *inelastic_e_out,
+                       const double *inelastic_mu, const int *cont_n_e_out, const double *cont_e_out,
+                       const double *cont_pdf, const double *cont_mu, int elastic_mode, int n_elastic_e_in,
+                       int n_elastic_mu, const double *elastic_e_in, const double *elastic_P,
+                       const double *elastic_mu, void **sab);
+/* calc_scattsab minus sab_egrid: scatt_mat[NE][G][order+1].  el_out / inel_out (nullable) receive
+ * the partial integrals of integrate_sab_el / integrate_sab_inel. */
+int ndppgpu_sab(void *sab, const double *e_bins, int n_bins, int scatt_type, int order, const double *Ein, int NE,
+                double *scatt_mat, double *el_out, double *inel_out);
+int ndppgpu_sab_dev(void *sab, const double *e_bins, int n_bins, int scatt_type, int order, const double *d_Ein,
+                    int NE, double *d_scatt_mat);
+int ndppgpu_sab_free(void *sab);
+
+/* ---- device micro-benchmark: sustained FP64 FMA rate of this GPU, used as the roofline
+ *      denominator (MEASURED_PEAKS.json holds no FP64 figure) ----------------------------------- */
+int ndppgpu_measure_fp64_peak(void *ctx, double seconds, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""ctypes binding of the C-ABI in include/ndppgpu.h (libndppgpu.so).
+
+This is the Python twin of the ISO_C_BINDING interface module the reference's Fortran driver would
+use.  Loading fails loudly when the library has not been built, and every entry
+point raises NdppGpuError on a non-zero status -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libndppgpu.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+# every symbol include/ndppgpu.h declares
+EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_stats", "ndppgpu_abi_version",
+           "ndppgpu_stream", "ndppgpu_nuclide_create", "ndppgpu_nuclide_add_reaction", "ndppgpu_convert_distro",
+           "ndppgpu_elastic", "ndppgpu_inelastic", "ndppgpu_elastic_dev", "ndppgpu_inelastic_dev",
+           "ndppgpu_nuclide_n_slots", "ndppgpu_nuclide_slot_info", "ndppgpu_nuclide_slot_row_np",
+           "ndppgpu_nuclide_get_table", "ndppgpu_nuclide_free", "ndppgpu_sab_create", "ndppgpu_sab", "ndppgpu_sab_dev",
+           "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak"]
+
+
+class NdppGpuError(RuntimeError):
+    pass
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("scatt_type", C.c_int), ("order", C.c_int), ("mu_bins", C.c_int), ("nuscatter", C.c_int),
+                ("ne_per_grp", C.c_int), ("adaptive_mu_its", C.c_int), ("adaptive_eout_its", C.c_int),
+                ("reserved", C.c_int), ("sab_threshold", C.c_double), ("brent_mu_thresh", C.c_double),
+                ("adaptive_mu_tol", C.c_double), ("adaptive_eout_tol", C.c_double)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+                ("launches", C.c_longlong), ("moment_evals", C.c_longlong), ("file4_calls", C.c_longlong),
+                ("file6_cm_points", C.c_longlong), ("file6_lab_calls", C.c_longlong), ("freegas_tasks", C.c_longlong),
+                ("sab_columns", C.c_longlong), ("file6_cm_ms", C.c_double), ("file6_cm_launches", C.c_longlong),
+                ("reserved", C.c_double * 6)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libndppgpu.so; raise if it is missing (build with `python -m ndpp_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise NdppGpuError(f"{SO_PATH} not found: build the CUDA library first (python ndpp_b200/build.py). "
+                           "ndpp_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.ndppgpu_init.argtypes = [i, C.POINTER(vp)]
+    L.ndppgpu_finalize.argtypes = [vp]
+    L.ndppgpu_last_error.argtypes = [vp, C.c_char_p, i]
+    L.ndppgpu_stats.argtypes = [vp, C.POINTER(StatsC), i]
+    L.ndppgpu_stream.argtypes = [vp]
+    L.ndppgpu_stream.restype = vp
+    L.ndppgpu_nuclide_create.argtypes = [vp, d, d, d, i, c_dp, c_dp, c_dp, i, C.POINTER(ParamsC), C.POINTER(vp)]
+    L.ndppgpu_nuclide_add_reaction.argtypes = [vp, i, i, d, i, i, i, i, i, i, c_dp, i, c_dp, i, c_dp, i, c_dp, c_ip,
+                                               c_ip, i, c_dp, i, c_dp, i]
+    L.ndppgpu_convert_distro.argtypes = [vp]
+    L.ndppgpu_elastic.argtypes = [vp, c_dp, i, c_dp]
+    L.ndppgpu_inelastic.argtypes = [vp, c_dp, i, c_dp, c_dp]
+    L.ndppgpu_elastic_dev.argtypes = [vp, vp, i, vp]
+    L.ndppgpu_inelastic_dev.argtypes = [vp, vp, i, vp, vp]
+    L.ndppgpu_nuclide_n_slots.argtypes = [vp]
+    L.ndppgpu_nuclide_slot_info.argtypes = [vp, i, c_ip]
+    L.ndppgpu_nuclide_slot_row_np.argtypes = [vp, i, i]
+    L.ndppgpu_nuclide_get_table.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_ip]
+    L.ndppgpu_nuclide_free.argtypes = [vp]
+    L.ndppgpu_sab_create.argtypes = [vp, d, d, d, d, i, i, i, i, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp, i,
+                                     i, i, c_dp, c_dp, c_dp, C.POINTER(vp)]
+    L.ndppgpu_sab.argtypes = [vp, c_dp, i, i, i, c_dp, i, c_dp, c_dp, c_dp]
+    L.ndppgpu_sab_dev.argtypes = [vp, c_dp, i, i, i, vp, i, vp]
+    L.ndppgpu_sab_free.argtypes = [vp]
+    L.ndppgpu_measure_fp64_peak.argtypes = [vp, d, C.POINTER(d)]
+    _lib = L
+    return L
+
+
+def f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+
+
+def i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32).ravel())
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def make_params(p) -> ParamsC:
+    return ParamsC(int(p.scatt_type), int(p.order), int(p.mu_bins), int(bool(p.nuscatter)), int(p.ne_per_grp),
+                   int(p.adaptive_mu_its), int(p.adaptive_eout_its), 0, float(p.sab_threshold),
+                   float(p.brent_mu_thresh), float(p.adaptive_mu_tol), float(p.adaptive_eout_tol))
+
+
+def last_error(ctx=None) -> str:
+    buf = C.create_string_buffer(1024)
+    load().ndppgpu_last_error(ctx, buf, 1024)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc, ctx=None):
+    if rc != 0:
+        raise NdppGpuError(last_error(ctx))
+
+
+class Context:
+    """One device context (ndppgpu_init / ndppgpu_finalize)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load()
+        self.h = C.c_void_p()
+        check(self.lib.ndppgpu_init(int(device), C.byref(self.h)))
+
+    def stats(self, reset=False) -> dict:
+        s = StatsC()
+        check(self.lib.ndppgpu_stats(self.h, C.byref(s), int(reset)), self.h)
+        return {k: getattr(s, k) for k, _ in StatsC._fields_ if k != "reserved"}
+
+    def measure_fp64_peak(self, seconds=0.5) -> float:
+        out = C.c_double(0.0)
+        check(self.lib.ndppgpu_measure_fp64_peak(self.h, float(seconds), C.byref(out)), self.h)
+        return out.value
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.ndppgpu_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            self.lib.ndppgpu_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -123,6 +123,7 @@ int ref_nuclide_interp_distro(void *nuc, int slot, double Ein, double *distro);
 int ref_nuclide_elastic(void *nuc, const double *Ein, int NE, double *el_mat, int n_threads);
 int ref_nuclide_inelastic(void *nuc, const double *Ein, int NE, double *inel_mat, double *nuinel_mat, int n_threads);
 void ref_nuclide_free(void *nuc);
+void ref_set_omp_chunk(int chunk);
 
 /* ---- S(a,b), src/sab.F90 + calc_scattsab (src/scatt.F90:543-596) ---- */
 void *ref_sab_create(double awr, double kT, double threshold_inelastic, double threshold_elastic, int n_inelastic_e_in,

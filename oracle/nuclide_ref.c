@@ -522,6 +522,11 @@ int ref_nuclide_interp_distro(void *h, int slot, double Ein, double *distro)
     return 0;
 }
 
+/* chunk of the E_in loops: 100 as src/scatt.F90:631,722; bench.py lowers it for its bounded samples
+ * (a few hundred points), which would otherwise fall into one or two chunks */
+static int g_omp_chunk = 100;
+void ref_set_omp_chunk(int chunk) { g_omp_chunk = chunk > 0 ? chunk : 100; }
+
 static int slot_order(ref_nuclide *nuc)
 {
     int i, order = 0;
@@ -538,7 +543,7 @@ int ref_nuclide_elastic(void *h, const double *Ein, int NE, double *el_mat, int 
     size_t col = (size_t)order * groups;
     (void)n_threads;
 
-#pragma omp parallel for schedule(dynamic, 100) num_threads(n_threads > 0 ? n_threads : 1)
+#pragma omp parallel for schedule(dynamic, g_omp_chunk) num_threads(n_threads > 0 ? n_threads : 1)
     for (iE = 1; iE <= NE; ++iE) {
         int irxn;
         double *out = el_mat + col * (iE - 1);
@@ -574,7 +579,7 @@ int ref_nuclide_inelastic(void *h, const double *Ein, int NE, double *inel_mat, 
 #pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
     {
         double *temp = (double *)malloc(sizeof(double) * col);
-#pragma omp for schedule(dynamic, 100)
+#pragma omp for schedule(dynamic, g_omp_chunk)
         for (iE = 1; iE <= NE; ++iE) {
             int irxn;
             size_t k;
