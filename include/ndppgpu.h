@@ -116,6 +116,13 @@ int ndppgpu_nuclide_slot_row_np(void *nuc, int slot, int iE /* 1-based */);
 /* row iE of the converted tables: distro[NP][M] (== Fortran data(M,NP)), Eouts/pdf/cdf[NP] */
 int ndppgpu_nuclide_get_table(void *nuc, int slot, int iE, double *distro, double *Eouts, double *pdf,
                               double *cdf, int *INTT);
+/* Overwrite row iE of a slot's converted table with host values distro[NP][M].  Lets the Fortran side
+ * keep convert_distro on the host (its tables then are bit-identical to the reference's own libm),
+ * and lets the parity tests separate the integrators from the table conversion. */
+int ndppgpu_nuclide_set_table(void *nuc, int slot, int iE, const double *distro);
+/* ScattData%interp_distro (src/scattdata_header.F90:391-499) of one slot at NE incoming energies:
+ * distro[NE][G][L], scaled by sigma_s * p_valid for non-elastic reactions exactly as the reference. */
+int ndppgpu_interp_distro(void *nuc, int slot, const double *Ein, int NE, double *distro);
 /* ScattData%clear for all slots (src/scatt.F90:153-155) */
 int ndppgpu_nuclide_free(void *nuc);
 
@@ -139,6 +146,11 @@ int ndppgpu_sab(void *sab, const double *e_bins, int n_bins, int scatt_type, int
 int ndppgpu_sab_dev(void *sab, const double *e_bins, int n_bins, int scatt_type, int order, const double *d_Ein,
                     int NE, double *d_scatt_mat);
 int ndppgpu_sab_free(void *sab);
+
+/* ---- leaf check of the device Legendre helpers: integrals[n][L] = calc_int_pn_tablelin(L, xlow, xhigh,
+ *      flow, fhigh) (src/legendre.F90:22) and pn[n][L] = calc_pn(l, xlow) (:349) for n inputs ------- */
+int ndppgpu_test_legendre(void *ctx, int n, int L, const double *xlow, const double *xhigh, const double *flow,
+                          const double *fhigh, double *integrals, double *pn);
 
 /* ---- device micro-benchmark: sustained FP64 FMA rate of this GPU, used as the roofline
  *      denominator (MEASURED_PEAKS.json holds no FP64 figure) ----------------------------------- */

@@ -23,7 +23,7 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_elastic", "ndppgpu_inelastic", "ndppgpu_elastic_dev", "ndppgpu_inelastic_dev",
            "ndppgpu_nuclide_n_slots", "ndppgpu_nuclide_slot_info", "ndppgpu_nuclide_slot_row_np",
            "ndppgpu_nuclide_get_table", "ndppgpu_nuclide_free", "ndppgpu_sab_create", "ndppgpu_sab", "ndppgpu_sab_dev",
-           "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak"]
+           "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table"]
 
 
 class NdppGpuError(RuntimeError):
@@ -83,6 +83,9 @@ def load() -> C.CDLL:
     L.ndppgpu_sab_dev.argtypes = [vp, c_dp, i, i, i, vp, i, vp]
     L.ndppgpu_sab_free.argtypes = [vp]
     L.ndppgpu_measure_fp64_peak.argtypes = [vp, d, C.POINTER(d)]
+    L.ndppgpu_interp_distro.argtypes = [vp, i, c_dp, i, c_dp]
+    L.ndppgpu_nuclide_set_table.argtypes = [vp, i, i, c_dp]
+    L.ndppgpu_test_legendre.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     _lib = L
     return L
 
@@ -137,6 +140,13 @@ class Context:
         out = C.c_double(0.0)
         check(self.lib.ndppgpu_measure_fp64_peak(self.h, float(seconds), C.byref(out)), self.h)
         return out.value
+
+    def test_legendre(self, L, xlow, xhigh, flow, fhigh):
+        xl, xh, fl, fh = f64(xlow), f64(xhigh), f64(flow), f64(fhigh)
+        integ, pn = np.empty((len(xl), L)), np.empty((len(xl), L))
+        check(self.lib.ndppgpu_test_legendre(self.h, len(xl), L, dp(xl), dp(xh), dp(fl), dp(fh), dp(integ), dp(pn)),
+              self.h)
+        return integ, pn
 
     @property
     def stream(self) -> int:

@@ -60,6 +60,7 @@ struct NucDev {
     const double* elastic;  // [n_grid]
     const double* e_bins;   // [n_bins]
     const double* mu;       // [M]
+    int* err;               // device error word: 1 = binary_search out of range (src/search.F90:36-38)
 };
 
 // binary_search_real, src/search.F90:21-71: 0-based lower index i with a[i] <= val < a[i+1]
@@ -171,7 +172,7 @@ __device__ __forceinline__ InterpInfo interp_info(const NucDev& nuc, const SlotD
         r.sigS = (1.0 - f) * s.sigma[ks] + f * s.sigma[ks + 1];
         if (r.sigS <= 0.0) return r;
         int iE;
-        if (Ein < s.e_grid[0]) iE = 0; else iE = binary_search(s.e_grid, s.NE, Ein);
+        if (Ein < s.e_grid[0]) iE = 0; else iE = binary_search(s.e_grid, s.NE, Ein, nuc.err);
         if (s.e_grid[iE] >= s.e_grid[iE + 1]) iE = iE + 1;
         r.iE = iE;
     }

@@ -125,7 +125,7 @@ struct Nuclide {
     ndppgpu_params p;
     double awr, kT, freegas_cutoff;
     std::vector<double> energy, elastic, e_bins, mu;
-    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_slots, d_el_ids, d_in_ids;
+    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_slots, d_el_ids, d_in_ids, d_err;
     NucDev dev{};
     std::vector<std::unique_ptr<HostRxn>> rxns;
     std::vector<std::unique_ptr<Slot>> slots;
@@ -229,7 +229,6 @@ int build_slot_device(Nuclide* n, Slot* s)
         if (upload(c, s->d_ad_energy, r->ad_energy.data(), r->ad_energy.size())) return 1;
         if (upload(c, s->d_ad_type, r->ad_type.data(), r->ad_type.size())) return 1;
         if (upload(c, s->d_ad_loc, r->ad_loc.data(), r->ad_loc.size())) return 1;
-        // one leading pad so that data(lc) reads (the reference's idata-1 look-back at lc = 0) stay in bounds
         if (upload(c, s->d_ad_data, r->ad_data.data(), r->ad_data.size())) return 1;
     }
     if (!s->edist_data.empty()) if (upload(c, s->d_ed_data, s->edist_data.data(), s->edist_data.size())) return 1;
@@ -315,6 +314,37 @@ __global__ void k_fp64_peak(double* out, int iters)
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// fatal_error of the reference's binary_search (src/search.F90:36-38), latched by the kernels
+int check_device_error(Nuclide* n)
+{
+    Ctx* c = n->ctx;
+    int e = 0;
+    CK(c, cudaMemcpyAsync(&e, n->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (e != 0) {
+        CK(c, cudaMemsetAsync(n->d_err.p, 0, sizeof(int), c->stream));
+        return fail(c, "Value outside of array during binary search");
+    }
+    return 0;
+}
+
+// leaf check of legendre.cuh (the reference tests calc_pn / calc_int_pn_tablelin the same way)
+__global__ void k_test_legendre(int n, int L, const double* __restrict__ xl, const double* __restrict__ xh,
+                                const double* __restrict__ fl, const double* __restrict__ fh, double* __restrict__ integ,
+                                double* __restrict__ pn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[NDPP_MAX_L], p[NDPP_MAX_L];
+    for (int l = 0; l < NDPP_MAX_L; ++l) { acc[l] = 0.0; p[l] = 0.0; }
+    Powers A, B;
+    make_powers(xl[i], A);
+    make_powers(xh[i], B);
+    add_int_pn_tablelin(L, xl[i], xh[i], fl[i], fh[i], A, B, acc);
+    calc_pn_all(L, xl[i], p);
+    for (int l = 0; l < L; ++l) { integ[(size_t)i * L + l] = acc[l]; pn[(size_t)i * L + l] = p[l]; }
+}
+
 int require_converted(Nuclide* n)
 {
     if (!n->converted) return fail(n->ctx, "ndppgpu: convert_distro must be called before integrating");
@@ -368,10 +398,10 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
     k_copy_top<<<1, 256, 0, c->stream>>>(d_Ein, NE, n->e_bins.back(), GL, d_out, nullptr);
     if (launch_check(c, "k_copy_top")) return 1;
     c->stats.moment_evals += (long long)NE * GL;
-    return 0;
+    return check_device_error(n);
 }
 
-int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double* d_nuout)
+int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double* d_nuout, int only_slot = -1)
 {
     Ctx* c = n->ctx;
     if (require_converted(n)) return 1;
@@ -382,8 +412,16 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     std::vector<std::unique_ptr<DevBuf>> slabs;
     std::vector<std::unique_ptr<UbScratch>> scratch;
     Timed tm(c, &c->pending_all);
+    std::vector<int> ids = n->in_ids;
+    DevBuf d_ids_override;
+    const int* d_ids = n->d_in_ids.as<int>();
+    if (only_slot >= 0) {
+        ids.assign(1, only_slot);
+        if (upload(c, d_ids_override, ids.data(), 1)) return 1;
+        d_ids = d_ids_override.as<int>();
+    }
 
-    for (int sid : n->in_ids) {
+    for (int sid : ids) {
         Slot* s = n->slots[sid].get();
         if (!s->has_edist) {
             if (!s->rxn->scatter_in_cm)
@@ -447,16 +485,15 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     while (smem > 200 * 1024 && nw > 1) { nw /= 2; smem = ((size_t)(2 + nw) * GL + nw) * sizeof(double); }
     if (smem > 200 * 1024) return fail(c, "ndppgpu: groups x orders too large for the shared-memory accumulator");
     CK(c, cudaFuncSetAttribute(k_inelastic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_inelastic<<<NE, nw * 32, smem, c->stream>>>(n->dev, n->d_slots.as<SlotDev>(), n->d_in_ids.as<int>(),
-                                                  (int)n->in_ids.size(), d_pre.as<const double*>(), d_Ein, NE, d_out,
-                                                  d_nuout);
+    k_inelastic<<<NE, nw * 32, smem, c->stream>>>(n->dev, n->d_slots.as<SlotDev>(), d_ids, (int)ids.size(),
+                                                  d_pre.as<const double*>(), d_Ein, NE, d_out, d_nuout);
     if (launch_check(c, "k_inelastic")) return 1;
     k_copy_top<<<1, 256, 0, c->stream>>>(d_Ein, NE, n->e_bins.back(), GL, d_out, d_nuout);
     if (launch_check(c, "k_copy_top")) return 1;
     CK(c, cudaStreamSynchronize(c->stream));  // scratch buffers are freed on scope exit
-    c->stats.file4_calls += 2LL * NE * (long long)n->in_ids.size();
+    c->stats.file4_calls += 2LL * NE * (long long)ids.size();
     c->stats.moment_evals += (long long)NE * GL * (d_nuout ? 2 : 1);
-    return 0;
+    return check_device_error(n);
 }
 
 // ---- S(a,b) ------------------------------------------------------------------------------------
@@ -616,8 +653,10 @@ int ndppgpu_nuclide_create(void* ctx, double awr, double kT, double freegas_cuto
     n->L = L; n->G = n_bins - 1;
     if (upload(c, n->d_energy, n->energy.data(), n->energy.size()) ||
         upload(c, n->d_elastic, n->elastic.data(), n->elastic.size()) ||
-        upload(c, n->d_e_bins, n->e_bins.data(), n->e_bins.size()) || upload(c, n->d_mu, n->mu.data(), n->mu.size()))
+        upload(c, n->d_e_bins, n->e_bins.data(), n->e_bins.size()) || upload(c, n->d_mu, n->mu.data(), n->mu.size()) ||
+        dev_alloc(c, n->d_err, sizeof(int)))
         return 1;
+    CK(c, cudaMemsetAsync(n->d_err.p, 0, sizeof(int), c->stream));
     NucDev& d = n->dev;
     d.n_grid = n_grid; d.n_bins = n_bins; d.M = M; d.L = L; d.G = n->G;
     d.ne_per_grp = params->ne_per_grp; d.adaptive_mu_its = params->adaptive_mu_its;
@@ -626,7 +665,7 @@ int ndppgpu_nuclide_create(void* ctx, double awr, double kT, double freegas_cuto
     d.sab_threshold = params->sab_threshold; d.brent_mu_thresh = params->brent_mu_thresh;
     d.adaptive_mu_tol = params->adaptive_mu_tol; d.adaptive_eout_tol = params->adaptive_eout_tol;
     d.energy = n->d_energy.as<double>(); d.elastic = n->d_elastic.as<double>();
-    d.e_bins = n->d_e_bins.as<double>(); d.mu = n->d_mu.as<double>();
+    d.e_bins = n->d_e_bins.as<double>(); d.mu = n->d_mu.as<double>(); d.err = n->d_err.as<int>();
     *nuc = n.release();
     return 0;
 }
@@ -755,6 +794,20 @@ int ndppgpu_nuclide_get_table(void* nuc, int slot, int iE, double* distro, doubl
     return 0;
 }
 
+int ndppgpu_nuclide_set_table(void* nuc, int slot, int iE, const double* distro)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n || slot < 0 || slot >= (int)n->slots.size() || !distro) return fail(n ? n->ctx : nullptr, "set_table: bad argument");
+    Ctx* c = n->ctx;
+    Slot* s = n->slots[slot].get();
+    if (!s->is_init || !n->converted || iE < 1 || iE > s->NE) return fail(c, "set_table: slot not converted or row out of range");
+    CK(c, cudaSetDevice(c->device));
+    const int M = n->p.mu_bins, off = s->row_off[iE - 1], NP = s->row_off[iE] - off;
+    CK(c, cudaMemcpy(s->d_tab.as<double>() + (size_t)off * M, distro, (size_t)NP * M * sizeof(double), cudaMemcpyHostToDevice));
+    c->stats.h2d_bytes += (double)NP * M * sizeof(double);
+    return 0;
+}
+
 int ndppgpu_elastic_dev(void* nuc, const double* d_Ein, int NE, double* d_el_mat)
 {
     Nuclide* n = (Nuclide*)nuc;
@@ -804,6 +857,46 @@ int ndppgpu_inelastic(void* nuc, const double* Ein, int NE, double* inel_mat, do
     if (nuinel_mat) CK(c, cudaMemcpyAsync(nuinel_mat, d_nu.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (double)(nout * sizeof(double) * (nuinel_mat ? 2 : 1));
+    return 0;
+}
+
+int ndppgpu_interp_distro(void* nuc, int slot, const double* Ein, int NE, double* distro)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n || !Ein || !distro) return fail(n ? n->ctx : nullptr, "ndppgpu_interp_distro: null argument");
+    Ctx* c = n->ctx;
+    if (slot < 0 || slot >= (int)n->slots.size() || !n->slots[slot]->is_init)
+        return fail(c, "ndppgpu_interp_distro: slot is not an initialised scattering reaction");
+    CK(c, cudaSetDevice(c->device));
+    if (NE <= 0) return 0;
+    if (n->slots[slot]->rxn->MT == 2 && n->freegas_cutoff > 0.0)
+        return fail(c, "ndppgpu_interp_distro: use ndppgpu_elastic for the free-gas elastic reaction");
+    DevBuf d_E, d_out;
+    const size_t nout = (size_t)NE * n->G * n->L;
+    if (upload(c, d_E, Ein, (size_t)NE) || dev_alloc(c, d_out, nout * sizeof(double))) return 1;
+    if (inelastic_dev(n, d_E.as<double>(), NE, d_out.as<double>(), nullptr, slot)) return 1;
+    CK(c, cudaMemcpy(distro, d_out.p, nout * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ndppgpu_test_legendre(void* ctx, int n, int L, const double* xlow, const double* xhigh, const double* flow,
+                          const double* fhigh, double* integrals, double* pn)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !xlow || !xhigh || !flow || !fhigh || !integrals || !pn) return fail(c, "ndppgpu_test_legendre: null argument");
+    if (L < 1 || L > NDPP_MAX_L) return fail(c, "ndppgpu_test_legendre: L outside 1..11");
+    CK(c, cudaSetDevice(c->device));
+    DevBuf a, b, fa, fb, oi, op;
+    if (upload(c, a, xlow, (size_t)n) || upload(c, b, xhigh, (size_t)n) || upload(c, fa, flow, (size_t)n) ||
+        upload(c, fb, fhigh, (size_t)n) || dev_alloc(c, oi, (size_t)n * L * sizeof(double)) ||
+        dev_alloc(c, op, (size_t)n * L * sizeof(double)))
+        return 1;
+    k_test_legendre<<<blocks_for(n, 128), 128, 0, c->stream>>>(n, L, a.as<double>(), b.as<double>(), fa.as<double>(),
+                                                               fb.as<double>(), oi.as<double>(), op.as<double>());
+    if (launch_check(c, "k_test_legendre")) return 1;
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(integrals, oi.p, (size_t)n * L * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(pn, op.p, (size_t)n * L * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -85,6 +85,18 @@ class DeviceNuclide:
               self.ctx.h)
         return d.reshape(NP, M).T.copy(), Eo, pdf, cdf, INTT.value
 
+    def set_table(self, s, iE, distro):
+        """Overwrite row iE (1-based) of slot s with distro (M, NP) as get_table returns it."""
+        d = np.ascontiguousarray(np.asarray(distro, dtype=np.float64).T)
+        check(self.lib.ndppgpu_nuclide_set_table(self.h, s, iE, dp(d.ravel())), self.ctx.h)
+
+    def interp_distro(self, s, Ein) -> np.ndarray:
+        """mySD % interp_distro (src/scattdata_header.F90:391) for slot s at every E_in: [NE][G][L]."""
+        Ein = f64(Ein)
+        out = np.empty((len(Ein), self.G, self.L))
+        check(self.lib.ndppgpu_interp_distro(self.h, s, dp(Ein), len(Ein), dp(out)), self.ctx.h)
+        return out
+
     # -- calc_elastic_grid / calc_inelastic_grid, host buffers -----------------------------------
     def elastic(self, Ein) -> np.ndarray:
         Ein = f64(Ein)
