@@ -159,7 +159,7 @@ struct FEmu {
 // group moments.  Warps take the NE_PER_GRP outgoing energies of the group round-robin; lanes run
 // over the M lab cosines in windows of 32 points / 31 segments.
 // Dynamic shared memory: maxU*(4 doubles + 2 ints) + ne_per_grp*L doubles.
-__global__ void k_file6_cm(NucDev nuc, SlotDev s, const double* __restrict__ Ein, UbDev ub, double* __restrict__ raw)
+__global__ void __launch_bounds__(128, 4) k_file6_cm(NucDev nuc, SlotDev s, const double* __restrict__ Ein, UbDev ub, double* __restrict__ raw)
 {
     extern __shared__ double sm[];
     const int g = blockIdx.x, iEin = blockIdx.y;
@@ -270,7 +270,8 @@ __global__ void k_file6_cm(NucDev nuc, SlotDev s, const double* __restrict__ Ein
                     }
                 }
                 const double fnext = __shfl_down_sync(0xffffffffu, fv, 1);
-                if (lane < 31 && p + 1 < M) {
+                // a segment whose two end values are zero adds exact zeros: skipped
+                if (lane < 31 && p + 1 < M && (fv != 0.0 || fnext != 0.0)) {
                     const double xh = mu_l_min + dmu * (double)(p + 1);
                     Powers A, B;
                     make_powers(x, A);

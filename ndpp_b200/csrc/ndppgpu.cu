@@ -71,6 +71,38 @@ int dev_alloc(Ctx* c, DevBuf& b, size_t bytes)
     return 0;
 }
 
+// Stream-ordered temporary (cudaMallocAsync pool with an unlimited release threshold): per-call
+// scratch is recycled without device synchronisation.
+struct TmpBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+    ~TmpBuf() { if (p) cudaFreeAsync(p, st); }
+    TmpBuf() = default;
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    template <class T> T* as() const { return (T*)p; }
+};
+
+int tmp_alloc(Ctx* c, TmpBuf& b, size_t bytes)
+{
+    if (b.p) { cudaFreeAsync(b.p, b.st); b.p = nullptr; }
+    b.bytes = bytes;
+    b.st = c->stream;
+    if (bytes == 0) return 0;
+    CK(c, cudaMallocAsync(&b.p, bytes, c->stream));
+    return 0;
+}
+
+template <class T> int tmp_upload(Ctx* c, TmpBuf& b, const T* h, size_t n)
+{
+    if (tmp_alloc(c, b, n * sizeof(T))) return 1;
+    if (n == 0) return 0;
+    CK(c, cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (double)(n * sizeof(T));
+    return 0;
+}
+
 template <class T> int upload(Ctx* c, DevBuf& b, const T* h, size_t n)
 {
     if (dev_alloc(c, b, n * sizeof(T))) return 1;
@@ -270,16 +302,16 @@ int launch_check(Ctx* c, const char* what)
 
 // unit-base scratch of one file-6 slot for one call
 struct UbScratch {
-    DevBuf n, f, info, eout, pdf, j1, r1, j2, r2;
+    TmpBuf n, f, info, eout, pdf, j1, r1, j2, r2;
     UbDev dev{};
     int alloc(Ctx* c, int NE, int maxU)
     {
         const size_t m = (size_t)NE * std::max(maxU, 1);
-        if (dev_alloc(c, n, NE * sizeof(int)) || dev_alloc(c, f, NE * sizeof(double)) ||
-            dev_alloc(c, info, NE * sizeof(InterpInfo)) || dev_alloc(c, eout, m * sizeof(double)) ||
-            dev_alloc(c, pdf, m * sizeof(double)) || dev_alloc(c, j1, m * sizeof(int)) ||
-            dev_alloc(c, r1, m * sizeof(double)) || dev_alloc(c, j2, m * sizeof(int)) ||
-            dev_alloc(c, r2, m * sizeof(double)))
+        if (tmp_alloc(c, n, NE * sizeof(int)) || tmp_alloc(c, f, NE * sizeof(double)) ||
+            tmp_alloc(c, info, NE * sizeof(InterpInfo)) || tmp_alloc(c, eout, m * sizeof(double)) ||
+            tmp_alloc(c, pdf, m * sizeof(double)) || tmp_alloc(c, j1, m * sizeof(int)) ||
+            tmp_alloc(c, r1, m * sizeof(double)) || tmp_alloc(c, j2, m * sizeof(int)) ||
+            tmp_alloc(c, r2, m * sizeof(double)))
             return 1;
         dev.maxU = std::max(maxU, 1);
         dev.n = n.as<int>(); dev.f = f.as<double>(); dev.info = info.as<InterpInfo>();
@@ -373,8 +405,8 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         if (n->p.adaptive_mu_its > FG_MAX_DEPTH - 2 || n->p.adaptive_eout_its > FG_MAX_DEPTH - 2)
             return fail(c, "ndppgpu: adaptive_*_its above the supported recursion depth");
         Slot* s = n->slots[n->el_ids.back()].get();
-        DevBuf idx, cnt, raw;
-        if (dev_alloc(c, idx, NE * sizeof(int)) || dev_alloc(c, cnt, sizeof(int))) return 1;
+        TmpBuf idx, cnt, raw;
+        if (tmp_alloc(c, idx, NE * sizeof(int)) || tmp_alloc(c, cnt, sizeof(int))) return 1;
         CK(c, cudaMemsetAsync(cnt.p, 0, sizeof(int), c->stream));
         k_fg_select<<<blocks_for(NE, 256), 256, 0, c->stream>>>(n->dev, s->dev, d_Ein, NE, idx.as<int>(), cnt.as<int>());
         if (launch_check(c, "k_fg_select")) return 1;
@@ -383,7 +415,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         CK(c, cudaStreamSynchronize(c->stream));
         if (n_idx > 0) {
             const int rows = s->iso_rows ? 1 : 2;
-            if (dev_alloc(c, raw, (size_t)n_idx * rows * GL * sizeof(double))) return 1;
+            if (tmp_alloc(c, raw, (size_t)n_idx * rows * GL * sizeof(double))) return 1;
             const long long tasks = (long long)n_idx * rows * GL;
             k_freegas<<<blocks_for(tasks, 64), 64, 0, c->stream>>>(n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows,
                                                                    raw.as<double>());
@@ -392,7 +424,6 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, raw.as<double>(), d_out);
             if (launch_check(c, "k_freegas_finish")) return 1;
             c->stats.freegas_tasks += tasks;
-            CK(c, cudaStreamSynchronize(c->stream));  // raw / idx are freed on scope exit
         }
     }
     k_copy_top<<<1, 256, 0, c->stream>>>(d_Ein, NE, n->e_bins.back(), GL, d_out, nullptr);
@@ -409,15 +440,15 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     const int G = n->G, L = n->L, GL = G * L, M = n->p.mu_bins;
     const size_t nslots = n->slots.size();
     std::vector<const double*> pre(nslots, nullptr);
-    std::vector<std::unique_ptr<DevBuf>> slabs;
+    std::vector<std::unique_ptr<TmpBuf>> slabs;
     std::vector<std::unique_ptr<UbScratch>> scratch;
     Timed tm(c, &c->pending_all);
     std::vector<int> ids = n->in_ids;
-    DevBuf d_ids_override;
+    TmpBuf d_ids_override;
     const int* d_ids = n->d_in_ids.as<int>();
     if (only_slot >= 0) {
         ids.assign(1, only_slot);
-        if (upload(c, d_ids_override, ids.data(), 1)) return 1;
+        if (tmp_upload(c, d_ids_override, ids.data(), 1)) return 1;
         d_ids = d_ids_override.as<int>();
     }
 
@@ -433,9 +464,9 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
             return fail(c, " Associated Edist and Adist, but not law 9: " + std::to_string(s->law) + ", " +
                                std::to_string(s->rxn->MT));
         if (cm && s->law == 9) return fail(c, "ndppgpu: law 9 in the centre-of-mass frame has no unit-base tables");
-        slabs.emplace_back(new DevBuf());
-        DevBuf& slab = *slabs.back();
-        if (dev_alloc(c, slab, (size_t)NE * GL * sizeof(double))) return 1;
+        slabs.emplace_back(new TmpBuf());
+        TmpBuf& slab = *slabs.back();
+        if (tmp_alloc(c, slab, (size_t)NE * GL * sizeof(double))) return 1;
         scratch.emplace_back(new UbScratch());
         UbScratch& ub = *scratch.back();
         const bool want_ub = (s->law != 9) || cm;
@@ -478,8 +509,8 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
         pre[sid] = slab.as<double>();
     }
 
-    DevBuf d_pre;
-    if (upload(c, d_pre, pre.data(), pre.size())) return 1;
+    TmpBuf d_pre;
+    if (tmp_upload(c, d_pre, pre.data(), pre.size())) return 1;
     int nw = 8;
     size_t smem = ((size_t)(2 + nw) * GL + nw) * sizeof(double);
     while (smem > 200 * 1024 && nw > 1) { nw /= 2; smem = ((size_t)(2 + nw) * GL + nw) * sizeof(double); }
@@ -490,7 +521,6 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     if (launch_check(c, "k_inelastic")) return 1;
     k_copy_top<<<1, 256, 0, c->stream>>>(d_Ein, NE, n->e_bins.back(), GL, d_out, d_nuout);
     if (launch_check(c, "k_copy_top")) return 1;
-    CK(c, cudaStreamSynchronize(c->stream));  // scratch buffers are freed on scope exit
     c->stats.file4_calls += 2LL * NE * (long long)ids.size();
     c->stats.moment_evals += (long long)NE * GL * (d_nuout ? 2 : 1);
     return check_device_error(n);
@@ -512,11 +542,11 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
     if (NE <= 0) return 0;
     const int G = n_bins - 1, L = order + 1, GL = G * L;
     Timed tm(c, &c->pending_all);
-    DevBuf d_bins, el, inel, distro;
-    if (upload(c, d_bins, e_bins, (size_t)n_bins)) return 1;
+    TmpBuf d_bins, el, inel, distro;
+    if (tmp_upload(c, d_bins, e_bins, (size_t)n_bins)) return 1;
     double* p_el = d_el_keep; double* p_inel = d_inel_keep;
-    if (!p_el) { if (dev_alloc(c, el, (size_t)NE * GL * sizeof(double))) return 1; p_el = el.as<double>(); }
-    if (!p_inel) { if (dev_alloc(c, inel, (size_t)NE * GL * sizeof(double))) return 1; p_inel = inel.as<double>(); }
+    if (!p_el) { if (tmp_alloc(c, el, (size_t)NE * GL * sizeof(double))) return 1; p_el = el.as<double>(); }
+    if (!p_inel) { if (tmp_alloc(c, inel, (size_t)NE * GL * sizeof(double))) return 1; p_inel = inel.as<double>(); }
     CK(c, cudaMemsetAsync(p_el, 0, (size_t)NE * GL * sizeof(double), c->stream));
     CK(c, cudaMemsetAsync(p_inel, 0, (size_t)NE * GL * sizeof(double), c->stream));
     if (scatt_type == 0) {  // SCATT_TYPE_LEGENDRE; TABULAR is a TODO in the reference (src/scatt.F90:579-588)
@@ -530,7 +560,7 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
                 s->dev, s->d_wgt.as<double>(), d_bins.as<double>(), n_bins, L, d_Ein, NE, p_inel);
             if (launch_check(c, "k_sab_inel_disc")) return 1;
         } else if (s->dev.secondary_mode == SAB_SECONDARY_CONT) {
-            if (dev_alloc(c, distro, (size_t)s->dev.n_in * GL * sizeof(double))) return 1;
+            if (tmp_alloc(c, distro, (size_t)s->dev.n_in * GL * sizeof(double))) return 1;
             k_sab_cont_table<<<blocks_for((long long)s->dev.n_in * GL, 128), 128, 0, c->stream>>>(
                 s->dev, d_bins.as<double>(), n_bins, L, distro.as<double>());
             if (launch_check(c, "k_sab_cont_table")) return 1;
@@ -543,7 +573,7 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
     if (launch_check(c, "k_sab_combine")) return 1;
     k_copy_last<<<4, 256, 0, c->stream>>>(GL, NE, d_out);
     if (launch_check(c, "k_copy_last")) return 1;
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));  // e_bins is caller-owned pageable memory
     c->stats.sab_columns += NE;
     c->stats.moment_evals += (long long)NE * GL;
     return 0;
@@ -571,6 +601,12 @@ int ndppgpu_init(int device, void** ctx)
     c->device = device;
     CK(nullptr, cudaSetDevice(device));
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CK(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ULL;  // never hand scratch memory back to the driver between calls
+        CK(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     *ctx = c.release();
     return 0;
 }
@@ -831,9 +867,9 @@ int ndppgpu_elastic(void* nuc, const double* Ein, int NE, double* el_mat)
     Ctx* c = n->ctx;
     CK(c, cudaSetDevice(c->device));
     if (NE <= 0) return 0;
-    DevBuf d_E, d_out;
+    TmpBuf d_E, d_out;
     const size_t nout = (size_t)NE * n->G * n->L;
-    if (upload(c, d_E, Ein, (size_t)NE) || dev_alloc(c, d_out, nout * sizeof(double))) return 1;
+    if (tmp_upload(c, d_E, Ein, (size_t)NE) || tmp_alloc(c, d_out, nout * sizeof(double))) return 1;
     if (elastic_dev(n, d_E.as<double>(), NE, d_out.as<double>())) return 1;
     CK(c, cudaMemcpyAsync(el_mat, d_out.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -848,10 +884,10 @@ int ndppgpu_inelastic(void* nuc, const double* Ein, int NE, double* inel_mat, do
     Ctx* c = n->ctx;
     CK(c, cudaSetDevice(c->device));
     if (NE <= 0) return 0;
-    DevBuf d_E, d_out, d_nu;
+    TmpBuf d_E, d_out, d_nu;
     const size_t nout = (size_t)NE * n->G * n->L;
-    if (upload(c, d_E, Ein, (size_t)NE) || dev_alloc(c, d_out, nout * sizeof(double))) return 1;
-    if (nuinel_mat && dev_alloc(c, d_nu, nout * sizeof(double))) return 1;
+    if (tmp_upload(c, d_E, Ein, (size_t)NE) || tmp_alloc(c, d_out, nout * sizeof(double))) return 1;
+    if (nuinel_mat && tmp_alloc(c, d_nu, nout * sizeof(double))) return 1;
     if (inelastic_dev(n, d_E.as<double>(), NE, d_out.as<double>(), nuinel_mat ? d_nu.as<double>() : nullptr)) return 1;
     CK(c, cudaMemcpyAsync(inel_mat, d_out.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (nuinel_mat) CK(c, cudaMemcpyAsync(nuinel_mat, d_nu.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
