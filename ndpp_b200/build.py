@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     srcs = sources()
     if not force and os.path.exists(SO) and all(os.path.getmtime(s) <= os.path.getmtime(SO) for s in srcs):
         return SO
-    cmd = [NVCC] + FLAGS + list(extra) + ["-o", SO, os.path.join(CSRC, "ndppgpu.cu")]
+    cmd = [NVCC] + FLAGS + list(extra) + os.environ.get("NDPP_NVCC_EXTRA", "").split() + \
+        ["-o", SO, os.path.join(CSRC, "ndppgpu.cu")]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -133,6 +133,21 @@ __device__ __forceinline__ double tolab(double R, double w)
     return (1.0 + R * w) / sqrt(1.0 + R * R + 2.0 * R * w);
 }
 
+// The same search for a caller that guarantees 0 <= a[0] <= val <= a[n-1] (non-negative values
+// order like their bit patterns, so the comparisons run on the integer pipe).  The reference's two
+// early-exit tests only shortcut cases in which the bisection reaches the same index, so they are
+// dropped; the bisection itself follows the reference's mid-point rule step for step.
+__device__ __forceinline__ int binary_search_nonneg(const double* __restrict__ a, int n, double val)
+{
+    int L = 0, R = n - 1;
+    const long long v = __double_as_longlong(val);
+    while (R - L > 1) {
+        const int mid = L + (R - L) / 2;
+        if (v >= __double_as_longlong(a[mid])) L = mid; else R = mid;
+    }
+    return L;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

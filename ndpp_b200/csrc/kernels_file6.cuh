@@ -159,13 +159,18 @@ struct FEmu {
 // group moments.  Warps take the NE_PER_GRP outgoing energies of the group round-robin; lanes run
 // over the M lab cosines in windows of 32 points / 31 segments.
 // Dynamic shared memory: maxU*(4 doubles + 2 ints) + ne_per_grp*L doubles.
-__global__ void __launch_bounds__(128, 4) k_file6_cm(NucDev nuc, SlotDev s, const double* __restrict__ Ein, UbDev ub, double* __restrict__ raw)
+#ifndef NDPP_F6_MINBLOCKS
+#define NDPP_F6_MINBLOCKS 4
+#endif
+template <int LT>
+__global__ void __launch_bounds__(128, NDPP_F6_MINBLOCKS) k_file6_cm(NucDev nuc, SlotDev s, const double* __restrict__ Ein, UbDev ub, double* __restrict__ raw)
 {
     extern __shared__ double sm[];
-    const int g = blockIdx.x, iEin = blockIdx.y;
+    const int g = blockIdx.y, iEin = blockIdx.x;  // E_in on x: up to 2^31-1 columns
     const int NPu = ub.n[iEin];
     if (NPu == 0) return;
-    const int M = nuc.M, L = nuc.L, K = nuc.ne_per_grp, nbins = nuc.n_bins;
+    constexpr int L = LT;
+    const int M = nuc.M, K = nuc.ne_per_grp, nbins = nuc.n_bins;
     const double E = Ein[iEin];
     const double awr = nuc.awr;
 
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(128, 4) k_file6_cm(NucDev nuc, SlotDev s, cons
                         int iEo;
                         if (Eo_cm <= eo[0]) iEo = 0;
                         else if (Eo_cm >= eo[NPu - 1]) iEo = NPu - 2;
-                        else iEo = binary_search(eo, NPu, Eo_cm);
+                        else iEo = binary_search_nonneg(eo, NPu, Eo_cm);
                         double fEo, pEo;
                         // the reference's INTT after unit-base interpolation is always lin-lin (:1716)
                         if (eo[iEo + 1] == eo[iEo]) { fEo = 0.0; pEo = pd[iEo]; }
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(128, 4) k_file6_cm(NucDev nuc, SlotDev s, cons
                     Powers A, B;
                     make_powers(x, A);
                     make_powers(xh, B);
-                    add_int_pn_tablelin(L, x, xh, fv, fnext, A, B, fEl);
+                    add_int_pn_tablelin<LT>(L, x, xh, fv, fnext, A, B, fEl);
                 }
             }
         }

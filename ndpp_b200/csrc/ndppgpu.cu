@@ -383,6 +383,35 @@ int require_converted(Nuclide* n)
     return 0;
 }
 
+// k_file6_cm is instantiated per number of Legendre orders (1..11)
+template <int LT>
+int launch_file6_cm_t(Ctx* c, dim3 grid, size_t smem, const NucDev& nd, const SlotDev& sd, const double* d_Ein,
+                      const UbDev& ub, double* raw)
+{
+    CK(c, cudaFuncSetAttribute(k_file6_cm<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_file6_cm<LT><<<grid, 128, smem, c->stream>>>(nd, sd, d_Ein, ub, raw);
+    return 0;
+}
+
+int launch_file6_cm(Ctx* c, int L, dim3 grid, size_t smem, const NucDev& nd, const SlotDev& sd, const double* d_Ein,
+                    const UbDev& ub, double* raw)
+{
+    switch (L) {
+    case 1: return launch_file6_cm_t<1>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 2: return launch_file6_cm_t<2>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 3: return launch_file6_cm_t<3>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 4: return launch_file6_cm_t<4>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 5: return launch_file6_cm_t<5>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 6: return launch_file6_cm_t<6>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 7: return launch_file6_cm_t<7>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 8: return launch_file6_cm_t<8>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 9: return launch_file6_cm_t<9>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 10: return launch_file6_cm_t<10>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    case 11: return launch_file6_cm_t<11>(c, grid, smem, nd, sd, d_Ein, ub, raw);
+    default: return fail(c, "ndppgpu: unsupported number of Legendre orders");
+    }
+}
+
 int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
 {
     Ctx* c = n->ctx;
@@ -478,10 +507,9 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
             CK(c, cudaMemsetAsync(slab.p, 0, slab.bytes, c->stream));
             const size_t smem = ub_smem + (size_t)n->p.ne_per_grp * L * sizeof(double) + 16;
             if (smem > 200 * 1024) return fail(c, "ndppgpu: outgoing-energy grid too large for shared memory");
-            CK(c, cudaFuncSetAttribute(k_file6_cm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 Timed t6(c, &c->pending_f6);
-                k_file6_cm<<<dim3(G, NE), 128, smem, c->stream>>>(n->dev, s->dev, d_Ein, ub.dev, slab.as<double>());
+                if (launch_file6_cm(c, L, dim3(NE, G), smem, n->dev, s->dev, d_Ein, ub.dev, slab.as<double>())) return 1;
             }
             if (launch_check(c, "k_file6_cm")) return 1;
             c->stats.file6_cm_launches++;

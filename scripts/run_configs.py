@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Runs every BASELINE.json configuration (C1-C5) on one B200 and writes the results table.
+
+For each configuration: the full-size GPU run (host buffers through the C-ABI; wall time and the
+library's CUDA-event kernel time), then the CPU oracle on a bounded sample of the same E_in points
+for parity (max errors, cells outside 1e-9 rel / 1e-12 abs, cells outside the round-off floor for
+Law-44 paths) and for the same-host CPU rate.  Output: gpurun_out/configs_<tag>.json (+ stdout).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ndpp_b200 import ace, egrid, scatt, synth  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+
+def parity(got, ref):
+    err = np.abs(got - ref)
+    strict = (err <= 1e-9 * np.abs(ref)) | (err <= 1e-12)
+    p0 = np.abs(ref[:, :, 0]).sum(axis=1)[:, None, None]
+    floor = err <= 1e-9 * np.abs(ref) + 1e-8 * p0 + 1e-12
+    with np.errstate(all="ignore"):
+        rel = np.where(np.abs(ref) > 1e-12, err / np.abs(ref), 0.0)
+    return {"cells": int(err.size), "max_abs": float(err.max()), "max_rel_where_ref_gt_1e-12": float(rel.max()),
+            "outside_1e-9rel_1e-12abs": int((~strict).sum()), "outside_roundoff_floor_1e-8_P0": int((~floor).sum())}
+
+
+def sample(arr, n, rng, e_top=None):
+    """Random sorted subset of indices.  Points above the top group edge copy the column of their
+    predecessor *in the grid they are part of* (src/scatt.F90:669,770), so they are left out of a
+    sub-sampled comparison."""
+    idx = np.arange(len(arr)) if e_top is None else np.nonzero(np.asarray(arr) <= e_top)[0]
+    if len(idx) <= n:
+        return idx
+    return np.sort(rng.choice(idx, n, replace=False))
+
+
+def run_nuclide(name, nuc, e_bins, params, Ein_el, Ein_inel, n_cpu, threads, ctx, rng):
+    GL = (len(e_bins) - 1) * (params.order + 1)
+    ctx.stats(reset=True)
+    t0 = time.perf_counter()
+    dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    el = dn.elastic(Ein_el)
+    inel = nu = None
+    if Ein_inel is not None and len(Ein_inel):
+        inel, nu = dn.inelastic(Ein_inel)
+    t_gpu = time.perf_counter() - t0
+    st = ctx.stats(reset=True)
+    evals = el.size + (inel.size if inel is not None else 0) + (nu.size if nu is not None else 0)
+    row = {"config": name, "G": len(e_bins) - 1, "L": params.order + 1, "M": params.mu_bins, "NE_el": len(Ein_el),
+           "NE_inel": 0 if Ein_inel is None else len(Ein_inel), "evals": int(evals), "gpu_setup_s": t_setup,
+           "gpu_wall_s": t_gpu, "gpu_kernel_ms": st["kernel_ms"], "gpu_evals_per_s_wall": evals / t_gpu,
+           "gpu_evals_per_s_kernel": evals / (st["kernel_ms"] * 1e-3) if st["kernel_ms"] else None,
+           "launches": st["launches"], "freegas_tasks": st["freegas_tasks"]}
+    # oracle on a sample
+    pyoracle.lib().ref_set_omp_chunk(1)
+    rn = pyoracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    ie = sample(Ein_el, n_cpu, rng, e_bins[-1])
+    pyoracle.freegas_counters(reset=True)
+    t0 = time.perf_counter()
+    rel = rn.elastic(Ein_el[ie], n_threads=threads)
+    t_cpu = time.perf_counter() - t0
+    cpu_evals = rel.size
+    row["n_fgk_n_sab_sample"] = list(pyoracle.freegas_counters(reset=True))
+    row["parity_elastic"] = parity(el[ie], rel)
+    if inel is not None:
+        ii = sample(Ein_inel, n_cpu, rng, e_bins[-1])
+        t0 = time.perf_counter()
+        ri, rnu = rn.inelastic(Ein_inel[ii], n_threads=threads)
+        t_cpu += time.perf_counter() - t0
+        cpu_evals += ri.size + (rnu.size if rnu is not None else 0)
+        row["parity_inelastic"] = parity(inel[ii], ri)
+        if nu is not None:
+            row["parity_nu_inelastic"] = parity(nu[ii], rnu)
+    row.update({"cpu_sample_points": int(len(ie)), "cpu_threads": threads, "cpu_s": t_cpu,
+                "cpu_evals_per_s": cpu_evals / t_cpu, "speedup_wall": (evals / t_gpu) / (cpu_evals / t_cpu)})
+    dn.clear()
+    rn.close()
+    return row
+
+
+def run_sab(name, sab, e_bins, order, n_cpu, ctx, rng):
+    Ein = egrid.sab_egrid(sab, e_bins)
+    ctx.stats(reset=True)
+    ds = scatt.DeviceSab(sab, ctx)
+    t0 = time.perf_counter()
+    got = ds.calc(e_bins, ace.SCATT_TYPE_LEGENDRE, order, Ein)
+    t_gpu = time.perf_counter() - t0
+    st = ctx.stats(reset=True)
+    ii = sample(Ein, n_cpu, rng)
+    # the last column copies its predecessor, so keep the two last points in the sample
+    ii = np.unique(np.concatenate([ii, [len(Ein) - 2, len(Ein) - 1]]))
+    t0 = time.perf_counter()
+    ref = pyoracle.sab_calc(sab, e_bins, order, Ein[ii])
+    t_cpu = time.perf_counter() - t0
+    row = {"config": name, "G": len(e_bins) - 1, "L": order + 1, "NE": len(Ein), "evals": int(got.size),
+           "gpu_wall_s": t_gpu, "gpu_kernel_ms": st["kernel_ms"], "gpu_evals_per_s_wall": got.size / t_gpu,
+           "gpu_evals_per_s_kernel": got.size / (st["kernel_ms"] * 1e-3), "launches": st["launches"],
+           "parity": parity(got[ii][:-1], ref[:-1]), "cpu_sample_points": int(len(ii)), "cpu_threads": 1,
+           "cpu_s": t_cpu, "cpu_evals_per_s": ref.size / t_cpu}
+    row["speedup_wall"] = row["gpu_evals_per_s_wall"] / row["cpu_evals_per_s"]
+    ds.clear()
+    return row
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tag", default="r1")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--c5-nuclides", type=int, default=12)
+    ap.add_argument("--cpu-points", type=int, default=64)
+    args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else None
+    threads = os.cpu_count() or 1
+    ctx = scatt.default_context()
+    rng = np.random.default_rng(1)
+    rows = []
+
+    def want(c):
+        return only is None or c in only
+
+    if want("C1"):
+        nuc, e_bins, params = synth.c1_fixture()
+        Ein = synth.c1_ein_grid(997)
+        rows.append(run_nuclide("C1 tests/test_scatt fixture (MT 51/52)", nuc, e_bins, params, Ein, Ein, 200, threads,
+                                ctx, rng))
+    if want("C2"):
+        nuc, e_bins, params, Eel, Einel = synth.c2_u238()
+        rows.append(run_nuclide("C2 U-238 shape, nuclide grid as E_in (20k)", nuc, e_bins, params, Eel, Einel,
+                                args.cpu_points * 4, threads, ctx, rng))
+    if want("C2g"):
+        nuc, e_bins, params, _, _ = synth.c2_u238()
+        Eel, Einel = egrid.create_Ein_grid(nuc, e_bins)
+        rows.append(run_nuclide("C2 U-238 shape, create_Ein_grid grids", nuc, e_bins, params, Eel, Einel,
+                                args.cpu_points * 4, threads, ctx, rng))
+    if want("C3"):
+        for kT, T in ((synth.KT_293K, 293.6), (synth.KT_600K, 600), (synth.KT_1200K, 1200)):
+            nuc, e_bins, params, Ein = synth.c3_h1_freegas(kT=kT)
+            rows.append(run_nuclide(f"C3 H-1 free gas {T} K", nuc, e_bins, params, Ein, None, max(8, args.cpu_points // 4),
+                                    threads, ctx, rng))
+    if want("C4"):
+        e_bins = synth.group_structure(70)
+        rows.append(run_sab("C4 H-in-H2O S(a,b) discrete skewed", synth.c4_sab("skewed"), e_bins, 5, 2000, ctx, rng))
+        rows.append(run_sab("C4 H-in-H2O S(a,b) continuous", synth.c4_sab("cont", n_eout=400), e_bins, 5, 2000, ctx, rng))
+        rows.append(run_sab("C4' graphite-like: equal + coherent elastic", synth.c4_sab("equal", elastic="coherent"),
+                            e_bins, 5, 2000, ctx, rng))
+    if want("C5"):
+        specs = synth.c5_library(300)
+        pick = specs[:args.c5_nuclides]
+        e_bins = synth.group_structure(70)
+        params = ace.Params(order=5, mu_bins=2001)
+        tot_ev, tot_gpu, tot_cpu_ev, tot_cpu_s, worst = 0, 0.0, 0, 0.0, 0
+        sub = []
+        for spec in pick:
+            nuc, Eel, Einel = synth.c5_nuclide(spec)
+            r = run_nuclide(f"C5 nuclide {spec[0]} ({spec[1]}, awr {spec[2]:.1f}, NE {spec[3]})", nuc, e_bins, params, Eel,
+                            Einel, 24, threads, ctx, rng)
+            sub.append(r)
+            tot_ev += r["evals"]; tot_gpu += r["gpu_wall_s"] + r["gpu_setup_s"]
+            tot_cpu_ev += r["cpu_evals_per_s"] * r["cpu_s"]; tot_cpu_s += r["cpu_s"]
+            for k in ("parity_elastic", "parity_inelastic"):
+                if k in r:
+                    worst = max(worst, r[k]["outside_roundoff_floor_1e-8_P0"])
+        rows.append({"config": f"C5 library, first {len(pick)} of 300 nuclides, P5, 1 GPU", "evals": tot_ev,
+                     "gpu_wall_s": tot_gpu, "gpu_evals_per_s_wall": tot_ev / tot_gpu,
+                     "cpu_evals_per_s": tot_cpu_ev / tot_cpu_s, "cpu_threads": threads,
+                     "cells_outside_floor": worst, "nuclides": sub})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", f"configs_{args.tag}.json")
+    json.dump(rows, open(path, "w"), indent=1)
+    for r in rows:
+        print(json.dumps({k: v for k, v in r.items() if k != "nuclides"}))
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()
