@@ -299,13 +299,16 @@ def run_b200(args):
     value = world * ev_step / (ms_step * 1e-3)
 
     # ---- e2e: calc_scatt with host (pinned) buffers ----------------------------------------------
+    # page-locked host buffers for the E_in grids and the result matrices (the contract's e2e path)
     h_Eel = torch.from_numpy(Ein_el).pin_memory().numpy()
     h_Ein = torch.from_numpy(Ein_inel).pin_memory().numpy()
+    h_el = torch.empty((len(Ein_el), GL), dtype=torch.float64).pin_memory().numpy()
+    h_inel = torch.empty((len(Ein_inel), GL), dtype=torch.float64).pin_memory().numpy()
 
     def step_e2e():
         dn2 = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
-        el = dn2.elastic(h_Eel)
-        inel, _ = dn2.inelastic(h_Ein, False)
+        el = dn2.elastic(h_Eel, out=h_el)
+        inel, _ = dn2.inelastic(h_Ein, False, out=h_inel)
         dn2.clear()
         return el, inel
 

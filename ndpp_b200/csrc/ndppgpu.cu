@@ -445,10 +445,32 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         if (n_idx > 0) {
             const int rows = s->iso_rows ? 1 : 2;
             if (tmp_alloc(c, raw, (size_t)n_idx * rows * GL * sizeof(double))) return 1;
-            const long long tasks = (long long)n_idx * rows * GL;
-            k_freegas<<<blocks_for(tasks, 64), 64, 0, c->stream>>>(n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows,
-                                                                   raw.as<double>());
-            if (launch_check(c, "k_freegas")) return 1;
+            const long long tasks = (long long)n_idx * GL;
+            // task list, heavy cells first
+            TmpBuf d_tasks, d_heads, d_counter, d_frames, d_nvals, d_nchilds;
+            if (tmp_alloc(c, d_tasks, (size_t)tasks * sizeof(int)) || tmp_alloc(c, d_heads, 2 * sizeof(int)) ||
+                tmp_alloc(c, d_counter, sizeof(unsigned long long)))
+                return 1;
+            CK(c, cudaMemsetAsync(d_heads.p, 0, 2 * sizeof(int), c->stream));
+            CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
+            k_fg_tasks<<<blocks_for(tasks, 256), 256, 0, c->stream>>>(n->dev, d_Ein, idx.as<int>(), n_idx,
+                                                                       d_tasks.as<int>(), d_heads.as<int>());
+            if (launch_check(c, "k_fg_tasks")) return 1;
+            // persistent warps with their level-parallel scratch (frontier 2^its frames x2, 2^(its+1) nodes)
+            cudaDeviceProp prop;
+            CK(c, cudaGetDeviceProperties(&prop, c->device));
+            const int blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * 3,
+                                                        (tasks + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
+            const size_t warps = (size_t)blocks * FG_WARPS_PER_BLOCK, cap = (size_t)1 << n->p.adaptive_mu_its;
+            if (tmp_alloc(c, d_frames, warps * 2 * cap * sizeof(FgFrame)) ||
+                tmp_alloc(c, d_nvals, warps * 2 * cap * sizeof(double)) ||
+                tmp_alloc(c, d_nchilds, warps * 2 * cap * sizeof(int)))
+                return 1;
+            k_freegas_warp<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
+                n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, d_tasks.as<int>(), tasks,
+                d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
+                raw.as<double>());
+            if (launch_check(c, "k_freegas_warp")) return 1;
             k_freegas_finish<<<blocks_for((long long)n_idx * 32, 128), 128, 0, c->stream>>>(
                 n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, raw.as<double>(), d_out);
             if (launch_check(c, "k_freegas_finish")) return 1;

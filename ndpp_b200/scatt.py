@@ -98,17 +98,25 @@ class DeviceNuclide:
         return out
 
     # -- calc_elastic_grid / calc_inelastic_grid, host buffers -----------------------------------
-    def elastic(self, Ein) -> np.ndarray:
+    def _out(self, out, n):
+        """Result buffer [n][G][L]; a caller-owned (e.g. page-locked) array may be passed in, as the
+        Fortran caller passes its own allocatable (src/scatt.F90:628,711)."""
+        if out is None:
+            return np.empty((n, self.G, self.L))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == n * self.G * self.L
+        return out
+
+    def elastic(self, Ein, out=None) -> np.ndarray:
         Ein = f64(Ein)
-        out = np.empty((len(Ein), self.G, self.L))
+        out = self._out(out, len(Ein))
         check(self.lib.ndppgpu_elastic(self.h, dp(Ein), len(Ein), dp(out)), self.ctx.h)
         return out
 
-    def inelastic(self, Ein, nuscatt=None):
+    def inelastic(self, Ein, nuscatt=None, out=None, nu_out=None):
         Ein = f64(Ein)
         nuscatt = self.params.nuscatter if nuscatt is None else nuscatt
-        out = np.empty((len(Ein), self.G, self.L))
-        nu = np.empty_like(out) if nuscatt else None
+        out = self._out(out, len(Ein))
+        nu = self._out(nu_out, len(Ein)) if nuscatt else None
         check(self.lib.ndppgpu_inelastic(self.h, dp(Ein), len(Ein), dp(out), dp(nu)), self.ctx.h)
         return out, nu
 
