@@ -226,19 +226,22 @@ def run_b200(args):
     dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
     d_Eel = torch.from_numpy(Ein_el).to(dev)
     d_Ein = torch.from_numpy(Ein_inel).to(dev)
-    d_el = torch.empty((len(Ein_el), GL), dtype=torch.float64, device=dev)
-    d_inel = torch.empty((len(Ein_inel), GL), dtype=torch.float64, device=dev)
+    n_el, n_in = len(Ein_el), len(Ein_inel)
+    max_el, max_in = n_el, n_in
+    if world > 1:
+        # the ranks' nuclides have the same shape but np.unique may drop a duplicate grid point on some
+        # of them: pad every slab to the largest so that one NCCL gather per matrix assembles them
+        sizes = torch.tensor([n_el, n_in], device=dev)
+        dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
+        max_el, max_in = int(sizes[0]), int(sizes[1])
+    d_el_pad = torch.zeros((max_el, GL), dtype=torch.float64, device=dev)
+    d_inel_pad = torch.zeros((max_in, GL), dtype=torch.float64, device=dev)
+    d_el, d_inel = d_el_pad[:n_el], d_inel_pad[:n_in]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     gather_el = gather_in = None
     if world > 1 and rank == 0:
-        gather_el = [torch.empty_like(d_el) for _ in range(world)]
-        gather_in = [torch.empty_like(d_inel) for _ in range(world)]
-    if world > 1:
-        # every rank's nuclide has the same grid sizes only if np.unique removed no duplicates
-        sizes = torch.tensor([len(Ein_el), len(Ein_inel)], device=dev)
-        allsz = [torch.empty_like(sizes) for _ in range(world)]
-        dist.all_gather(allsz, sizes)
-        same = all(bool((s == allsz[0]).all()) for s in allsz)
+        gather_el = [torch.empty_like(d_el_pad) for _ in range(world)]
+        gather_in = [torch.empty_like(d_inel_pad) for _ in range(world)]
 
     def step_device():
         with torch.cuda.stream(lib_stream):
@@ -246,12 +249,10 @@ def run_b200(args):
         dn.elastic_dev(d_Eel, d_el)
         dn.inelastic_dev(d_Ein, d_inel)
         if world > 1:
-            lib_stream.synchronize()
-            if same:
-                dist.gather(d_el, gather_el, dst=0)
-                dist.gather(d_inel, gather_in, dst=0)
-            else:  # ragged: exchange as padded point-to-point sends
-                dist.barrier()
+            torch.cuda.current_stream().wait_stream(lib_stream)
+            dist.gather(d_el_pad, gather_el, dst=0)
+            dist.gather(d_inel_pad, gather_in, dst=0)
+            lib_stream.wait_stream(torch.cuda.current_stream())
 
     def timed(fn, steps):
         torch.cuda.synchronize()

@@ -52,10 +52,11 @@ int fail(Ctx* c, const std::string& msg)
                                  std::to_string(__LINE__) + ")");                                           \
     } while (0)
 
-struct DevBuf {  // owning device allocation
+struct DevBuf {  // owning device allocation (stream-ordered pool: no device-wide sync on free)
     void* p = nullptr;
     size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -64,10 +65,11 @@ struct DevBuf {  // owning device allocation
 
 int dev_alloc(Ctx* c, DevBuf& b, size_t bytes)
 {
-    if (b.p) { cudaFree(b.p); b.p = nullptr; }
+    if (b.p) { cudaFreeAsync(b.p, b.st); b.p = nullptr; }
     b.bytes = bytes;
+    b.st = c->stream;
     if (bytes == 0) return 0;
-    CK(c, cudaMalloc(&b.p, bytes));
+    CK(c, cudaMallocAsync(&b.p, bytes, c->stream));
     return 0;
 }
 
