@@ -446,8 +446,9 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         CK(c, cudaStreamSynchronize(c->stream));
         if (n_idx > 0) {
             const int rows = s->iso_rows ? 1 : 2;
-            if (tmp_alloc(c, raw, (size_t)n_idx * rows * GL * sizeof(double))) return 1;
-            const long long tasks = (long long)n_idx * GL;
+            if (tmp_alloc(c, raw, (size_t)n_idx * rows * GL * 5 * sizeof(double))) return 1;
+            const long long tasks = (long long)n_idx * GL * 5;
+            if (tasks > 2000000000LL) return fail(c, "ndppgpu: too many free-gas cells in one call; split the E_in grid");
             // task list, heavy cells first
             TmpBuf d_tasks, d_heads, d_counter, d_frames, d_nvals, d_nchilds;
             if (tmp_alloc(c, d_tasks, (size_t)tasks * sizeof(int)) || tmp_alloc(c, d_heads, 2 * sizeof(int)) ||
