@@ -149,6 +149,10 @@ int ndppgpu_sab_free(void *sab);
 
 /* ---- leaf check of the device Legendre helpers: integrals[n][L] = calc_int_pn_tablelin(L, xlow, xhigh,
  *      flow, fhigh) (src/legendre.F90:22) and pn[n][L] = calc_pn(l, xlow) (:349) for n inputs ------- */
+/* Self-test of the shared-reciprocal division (csrc/legendre.cuh: FastDiv) against the IEEE operator on
+ * per_thread random operand pairs per GPU thread.  counts2 = {pairs, mismatches}; mismatches must be zero. */
+int ndppgpu_test_exact_math(void *ctx, unsigned long long seed, int per_thread, unsigned long long *counts2);
+
 int ndppgpu_test_legendre(void *ctx, int n, int L, const double *xlow, const double *xhigh, const double *flow,
                           const double *fhigh, double *integrals, double *pn);
 

@@ -23,7 +23,8 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_elastic", "ndppgpu_inelastic", "ndppgpu_elastic_dev", "ndppgpu_inelastic_dev",
            "ndppgpu_nuclide_n_slots", "ndppgpu_nuclide_slot_info", "ndppgpu_nuclide_slot_row_np",
            "ndppgpu_nuclide_get_table", "ndppgpu_nuclide_free", "ndppgpu_sab_create", "ndppgpu_sab", "ndppgpu_sab_dev",
-           "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table"]
+           "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
+           "ndppgpu_test_exact_math"]
 
 
 class NdppGpuError(RuntimeError):
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
     L.ndppgpu_interp_distro.argtypes = [vp, i, c_dp, i, c_dp]
     L.ndppgpu_nuclide_set_table.argtypes = [vp, i, i, c_dp]
     L.ndppgpu_test_legendre.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.ndppgpu_test_exact_math.argtypes = [vp, C.c_ulonglong, i, C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 
@@ -147,6 +149,11 @@ class Context:
         check(self.lib.ndppgpu_test_legendre(self.h, len(xl), L, dp(xl), dp(xh), dp(fl), dp(fh), dp(integ), dp(pn)),
               self.h)
         return integ, pn
+
+    def test_exact_math(self, seed=1, per_thread=2000):
+        out = (C.c_ulonglong * 2)()
+        check(self.lib.ndppgpu_test_exact_math(self.h, int(seed), int(per_thread), out), self.h)
+        return {"pairs": out[0], "mismatch": out[1]}
 
     @property
     def stream(self) -> int:

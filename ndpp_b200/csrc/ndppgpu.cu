@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -20,6 +21,7 @@
 #include "kernels_convert.cuh"
 #include "kernels_file4.cuh"
 #include "kernels_file6.cuh"
+#include "kernels_file6_ws.cuh"
 #include "kernels_freegas.cuh"
 #include "kernels_sab.cuh"
 
@@ -35,6 +37,9 @@ struct Ctx {
     std::string err;
     ndppgpu_stats_t stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
+    int sm_count = 148;
+    bool f6_solo = false;    // NDPPGPU_F6_SOLO=1: one role per warp on the same tables (A/B measurement)
+    bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
 };
 
 int fail(Ctx* c, const std::string& msg)
@@ -159,7 +164,7 @@ struct Nuclide {
     ndppgpu_params p;
     double awr, kT, freegas_cutoff;
     std::vector<double> energy, elastic, e_bins, mu;
-    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_slots, d_el_ids, d_in_ids, d_err;
+    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_rmu, d_slots, d_el_ids, d_in_ids, d_err;
     NucDev dev{};
     std::vector<std::unique_ptr<HostRxn>> rxns;
     std::vector<std::unique_ptr<Slot>> slots;
@@ -348,6 +353,30 @@ __global__ void k_fp64_peak(double* out, int iters)
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// FastDiv (shared-reciprocal division, legendre.cuh) against the plain operator on random operands spread
+// over many binades, zero dividends included.  counts[0] = pairs tried, counts[1] = mismatches.
+__global__ void k_test_exact_math(unsigned long long seed, int per_thread, unsigned long long* __restrict__ counts)
+{
+    unsigned long long st = seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    auto next = [&st]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    unsigned long long bad = 0;
+    for (int i = 0; i < per_thread; ++i) {
+        const unsigned long long a = next(), b = next();
+        const int ea = 1023 + (int)(next() % 121) - 60, eb = 1023 + (int)(next() % 121) - 60;
+        double x = __longlong_as_double((long long)((a & 0x800FFFFFFFFFFFFFULL) | ((unsigned long long)ea << 52)));
+        const double d = __longlong_as_double((long long)((b & 0x800FFFFFFFFFFFFFULL) | ((unsigned long long)eb << 52)));
+        if ((i & 1023) == 0) x = 0.0;
+        FastDiv fd;
+        fd.set(d);
+        if (__double_as_longlong(fd(x)) != __double_as_longlong(x / d)) ++bad;
+    }
+    atomicAdd(&counts[0], (unsigned long long)per_thread);
+    atomicAdd(&counts[1], bad);
+}
+
 // fatal_error of the reference's binary_search (src/search.F90:36-38), latched by the kernels
 int check_device_error(Nuclide* n)
 {
@@ -412,6 +441,88 @@ int launch_file6_cm(Ctx* c, int L, dim3 grid, size_t smem, const NucDev& nd, con
     case 11: return launch_file6_cm_t<11>(c, grid, smem, nd, sd, d_Ein, ub, raw);
     default: return fail(c, "ndppgpu: unsupported number of Legendre orders");
     }
+}
+
+// warp-specialised producer / consumer version (kernels_file6_ws.cuh)
+struct F6WsArgs {
+    const UbRec* rec; const int* sorted; const double* femu; const double* rmu; const int* act;
+    int a0, na;
+    unsigned long long* counter;
+};
+
+template <int LT>
+int launch_file6_ws_t(Ctx* c, int blocks, const NucDev& nd, const double* d_Ein, const UbDev& ub, const F6WsArgs& a,
+                      double* raw)
+{
+    if (c->f6_solo)
+        k_file6_cm_solo<LT><<<4 * c->sm_count, 128, 0, c->stream>>>(nd, d_Ein, ub, a.rec, a.sorted, a.femu, a.rmu, a.act,
+                                                                     a.a0, a.na, a.counter, raw);
+    else
+        k_file6_cm_ws<LT><<<blocks, F6_THREADS, 0, c->stream>>>(nd, d_Ein, ub, a.rec, a.sorted, a.femu, a.rmu, a.act,
+                                                                a.a0, a.na, a.counter, raw);
+    return 0;
+}
+
+int launch_file6_ws(Ctx* c, int L, int blocks, const NucDev& nd, const double* d_Ein, const UbDev& ub,
+                    const F6WsArgs& a, double* raw)
+{
+    switch (L) {
+    case 1: return launch_file6_ws_t<1>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 2: return launch_file6_ws_t<2>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 3: return launch_file6_ws_t<3>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 4: return launch_file6_ws_t<4>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 5: return launch_file6_ws_t<5>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 6: return launch_file6_ws_t<6>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 7: return launch_file6_ws_t<7>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 8: return launch_file6_ws_t<8>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 9: return launch_file6_ws_t<9>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 10: return launch_file6_ws_t<10>(c, blocks, nd, d_Ein, ub, a, raw);
+    case 11: return launch_file6_ws_t<11>(c, blocks, nd, d_Ein, ub, a, raw);
+    default: return fail(c, "ndppgpu: unsupported number of Legendre orders");
+    }
+}
+
+struct F6WsScratch { TmpBuf rec, sorted, femu, act, n_act, counter; };
+
+// integrate_file6_cm_leg for every active E_in of the call: active list, then per batch of E_in (sized so
+// that the materialised unit-base tables fit the scratch budget) records + tables + the pipeline kernel.
+int file6_cm_ws(Ctx* c, Nuclide* n, Slot* s, const double* d_Ein, int NE, const UbDev& ub, F6WsScratch& w, double* raw)
+{
+    const int G = n->G, L = n->L, M = n->p.mu_bins;
+    if (tmp_alloc(c, w.act, NE * sizeof(int)) || tmp_alloc(c, w.n_act, sizeof(int)) ||
+        tmp_alloc(c, w.counter, sizeof(unsigned long long)))
+        return 1;
+    k_f6_active<<<1, 1024, 0, c->stream>>>(ub.n, NE, w.act.as<int>(), w.n_act.as<int>());
+    if (launch_check(c, "k_f6_active")) return 1;
+    int n_act = 0;
+    CK(c, cudaMemcpyAsync(&n_act, w.n_act.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (n_act == 0) return 0;
+    size_t free_b = 0, total_b = 0;
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_ein = (size_t)ub.maxU * M * sizeof(double);
+    const size_t budget = std::min<size_t>((size_t)8 << 30, std::max<size_t>(free_b / 4, per_ein));
+    const int nb = (int)std::min<size_t>({(size_t)n_act, std::max<size_t>(budget / per_ein, 1), (size_t)65535});
+    if (tmp_alloc(c, w.rec, (size_t)nb * ub.maxU * sizeof(UbRec)) || tmp_alloc(c, w.sorted, nb * sizeof(int)) ||
+        tmp_alloc(c, w.femu, (size_t)nb * per_ein))
+        return 1;
+    for (int a0 = 0; a0 < n_act; a0 += nb) {
+        const int na = std::min(nb, n_act - a0);
+        CK(c, cudaMemsetAsync(w.counter.p, 0, sizeof(unsigned long long), c->stream));
+        k_f6_records<<<na, 128, 0, c->stream>>>(ub, w.act.as<int>(), a0, w.rec.as<UbRec>(), w.sorted.as<int>());
+        if (launch_check(c, "k_f6_records")) return 1;
+        k_f6_femu<<<dim3(blocks_for(M, 256), ub.maxU, na), 256, 0, c->stream>>>(n->dev, s->dev, ub, w.act.as<int>(), a0,
+                                                                                w.femu.as<double>());
+        if (launch_check(c, "k_f6_femu")) return 1;
+        F6WsArgs a{w.rec.as<UbRec>(), w.sorted.as<int>(), w.femu.as<double>(), n->d_rmu.as<double>(), w.act.as<int>(),
+                   a0, na, w.counter.as<unsigned long long>()};
+        const long long pairs = (long long)na * G;
+        const int blocks = (int)std::min<long long>((long long)F6_BLOCKS_PER_SM * c->sm_count,
+                                                    (pairs + F6_CONS - 1) / F6_CONS);
+        if (launch_file6_ws(c, L, blocks, n->dev, d_Ein, ub, a, raw)) return 1;
+        if (launch_check(c, "k_file6_cm_ws")) return 1;
+    }
+    return 0;
 }
 
 int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
@@ -496,6 +607,7 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     std::vector<const double*> pre(nslots, nullptr);
     std::vector<std::unique_ptr<TmpBuf>> slabs;
     std::vector<std::unique_ptr<UbScratch>> scratch;
+    std::vector<std::unique_ptr<F6WsScratch>> ws_scratch;
     Timed tm(c, &c->pending_all);
     std::vector<int> ids = n->in_ids;
     TmpBuf d_ids_override;
@@ -530,13 +642,17 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
         const size_t ub_smem = (size_t)ub.dev.maxU * (4 * sizeof(double) + 2 * sizeof(int));
         if (cm) {
             CK(c, cudaMemsetAsync(slab.p, 0, slab.bytes, c->stream));
-            const size_t smem = ub_smem + (size_t)n->p.ne_per_grp * L * sizeof(double) + 16;
-            if (smem > 200 * 1024) return fail(c, "ndppgpu: outgoing-energy grid too large for shared memory");
-            {
+            if (c->f6_legacy) {
+                const size_t smem = ub_smem + (size_t)n->p.ne_per_grp * L * sizeof(double) + 16;
+                if (smem > 200 * 1024) return fail(c, "ndppgpu: outgoing-energy grid too large for shared memory");
                 Timed t6(c, &c->pending_f6);
                 if (launch_file6_cm(c, L, dim3(NE, G), smem, n->dev, s->dev, d_Ein, ub.dev, slab.as<double>())) return 1;
+                if (launch_check(c, "k_file6_cm")) return 1;
+            } else {
+                ws_scratch.emplace_back(new F6WsScratch());
+                Timed t6(c, &c->pending_f6);
+                if (file6_cm_ws(c, n, s, d_Ein, NE, ub.dev, *ws_scratch.back(), slab.as<double>())) return 1;
             }
-            if (launch_check(c, "k_file6_cm")) return 1;
             c->stats.file6_cm_launches++;
             c->stats.file6_cm_points += (long long)NE * G * n->p.ne_per_grp * M;  // upper bound, see DESIGN.md
             k_file6_finish<<<blocks_for((long long)NE * 32, 128), 128, 0, c->stream>>>(n->dev, ub.dev, NE,
@@ -654,6 +770,13 @@ int ndppgpu_init(int device, void** ctx)
     c->device = device;
     CK(nullptr, cudaSetDevice(device));
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        const char* e = std::getenv("NDPPGPU_F6_LEGACY");
+        c->f6_legacy = e && e[0] == '1';
+        e = std::getenv("NDPPGPU_F6_SOLO");
+        c->f6_solo = e && e[0] == '1';
+    }
     {
         cudaMemPool_t pool;
         CK(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -743,9 +866,11 @@ int ndppgpu_nuclide_create(void* ctx, double awr, double kT, double freegas_cuto
     if (upload(c, n->d_energy, n->energy.data(), n->energy.size()) ||
         upload(c, n->d_elastic, n->elastic.data(), n->elastic.size()) ||
         upload(c, n->d_e_bins, n->e_bins.data(), n->e_bins.size()) || upload(c, n->d_mu, n->mu.data(), n->mu.size()) ||
-        dev_alloc(c, n->d_err, sizeof(int)))
+        dev_alloc(c, n->d_err, sizeof(int)) || dev_alloc(c, n->d_rmu, (size_t)M * sizeof(double)))
         return 1;
     CK(c, cudaMemsetAsync(n->d_err.p, 0, sizeof(int), c->stream));
+    k_rmu<<<blocks_for(M, 256), 256, 0, c->stream>>>(n->d_mu.as<double>(), M, n->d_rmu.as<double>());
+    if (launch_check(c, "k_rmu")) return 1;
     NucDev& d = n->dev;
     d.n_grid = n_grid; d.n_bins = n_bins; d.M = M; d.L = L; d.G = n->G;
     d.ne_per_grp = params->ne_per_grp; d.adaptive_mu_its = params->adaptive_mu_its;
@@ -986,6 +1111,21 @@ int ndppgpu_test_legendre(void* ctx, int n, int L, const double* xlow, const dou
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaMemcpy(integrals, oi.p, (size_t)n * L * sizeof(double), cudaMemcpyDeviceToHost));
     CK(c, cudaMemcpy(pn, op.p, (size_t)n * L * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ndppgpu_test_exact_math(void* ctx, unsigned long long seed, int per_thread, unsigned long long* counts2)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !counts2) return fail(c, "ndppgpu_test_exact_math: null argument");
+    CK(c, cudaSetDevice(c->device));
+    DevBuf d;
+    if (dev_alloc(c, d, 2 * sizeof(unsigned long long))) return 1;
+    CK(c, cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    k_test_exact_math<<<4 * c->sm_count, 256, 0, c->stream>>>(seed, per_thread, d.as<unsigned long long>());
+    if (launch_check(c, "k_test_exact_math")) return 1;
+    CK(c, cudaMemcpyAsync(counts2, d.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -302,3 +302,32 @@ def test_errors_are_loud(scatt):
     with pytest.raises(NdppGpuError, match="binary search"):
         dn.inelastic(np.array([2.7]))   # above the last tabulated adist energy: the reference aborts (search.F90:36-38)
     assert np.all(np.isfinite(dn.inelastic(np.array([2.2]))[0]))       # the latch was cleared
+
+
+@pytest.mark.parametrize("order", [7, 5])
+def test_file6_cm_ws_bit_identical_to_one_role_kernel(scatt, order, monkeypatch):
+    """The warp-specialised producer/consumer kernel (k_file6_cm_ws) re-organises the work of
+    k_file6_cm, not its arithmetic: both must give the same bits on the Law-44 continuum."""
+    from ndpp_b200.capi import Context
+    nuc = small_heavy(n_grid=600)
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=order)
+    thr = min(nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT == ace.N_NC)
+    Ein = nuc.energy[nuc.energy >= thr][::3]
+    outs = []
+    for legacy in ("1", "0"):
+        monkeypatch.setenv("NDPPGPU_F6_LEGACY", legacy)
+        ctx = Context(-1)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        slot = [s for s in range(dn.n_slots) if dn.slot_info(s)["is_init"] and dn.slot_info(s)["law"] == 44][0]
+        outs.append(dn.interp_distro(slot, Ein))
+        dn.clear()
+    assert np.any(outs[0] != 0.0)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_exact_math_sequences(scatt):
+    """FastDiv (nvcc's own division sequence with the reciprocal refinement hoisted) must reproduce
+    `/` bit for bit, zero dividends and distant binades included."""
+    r = scatt.default_context().test_exact_math(seed=20261018, per_thread=4000)
+    assert r["pairs"] > 5e8 and r["mismatch"] == 0, r
