@@ -318,3 +318,24 @@ def c5_nuclide(spec, seed=SEED0 + 5):
     inel = [nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT != ELASTIC]
     Ein_inel = nuc.energy[nuc.energy >= min(inel)].copy() if inel else None
     return nuc, Ein_el, Ein_inel
+
+
+def c5_shape(spec, e_max=20.0):
+    """library.NuclideShape of a C5 nuclide from its spec alone (no tables are generated): every rank
+    plans the whole library without building the nuclides it does not own."""
+    from .library import NuclideShape
+    i, shape, awr, ne = spec
+    awr = max(awr, 1.0001)
+    nlev = {"light": 0, "medium": 10, "heavy": 40}[shape]
+    first = 0.0449 if shape == "heavy" else 0.5
+    step = 0.028 if shape == "heavy" else 0.15
+    q_cont = -1.2 if shape == "heavy" else -3.0
+    lev = tuple((awr + 1.0) / awr * (first + step * k) for k in range(nlev))
+    cont = (awr + 1.0) / awr * abs(q_cont) if shape != "light" else None
+    thr = [x for x in lev] + ([cont] if cont is not None else [])
+    n_inel = 0
+    if thr:
+        frac = np.log(e_max / min(thr)) / np.log(e_max / 1.0e-11)
+        n_inel = max(1, int(ne * frac))
+    return NuclideShape(index=i, n_el=ne, n_inel=n_inel, level_thresholds=lev, cont_threshold=cont, e_lo=1.0e-11,
+                        e_hi=e_max)
