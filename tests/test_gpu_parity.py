@@ -331,3 +331,34 @@ def test_exact_math_sequences(scatt):
     `/` bit for bit, zero dividends and distant binades included."""
     r = scatt.default_context().test_exact_math(seed=20261018, per_thread=4000)
     assert r["pairs"] > 5e8 and r["mismatch"] == 0, r
+
+
+def test_against_committed_golden_vectors(scatt):
+    """CUDA path vs tests/golden/oracle_vectors.npz (oracle outputs committed with scripts/make_golden.py):
+    strict 1e-9 / 1e-12 where no libm transcendental sits between input and moment, round-off floor for
+    the Law 44 paths."""
+    import os
+    from ndpp_b200 import egrid
+    v = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.npz"))
+    nuc, e_bins, params = synth.c1_fixture()
+    dn = scatt.DeviceNuclide(nuc, e_bins, params)
+    assert_parity(dn.elastic(v["c1_Ein"]), v["c1_elastic"], what="golden C1 elastic")
+    gi, gn = dn.inelastic(v["c1_Ein"])
+    assert_parity_floor(gi, v["c1_inelastic"], what="golden C1 inelastic")
+    assert_parity_floor(gn, v["c1_nu_inelastic"], what="golden C1 nu-inelastic")
+    dn.clear()
+    dn = scatt.DeviceNuclide(small_heavy(), synth.group_structure(70), ace.Params(order=7))
+    assert_parity(dn.elastic(v["heavy_Eel"]), v["heavy_elastic"], what="golden heavy elastic")
+    assert_parity_floor(dn.inelastic(v["heavy_Ein"])[0], v["heavy_inelastic"], what="golden heavy inelastic")
+    dn.clear()
+    nuc, e_bins, params, _ = synth.c3_h1_freegas(n_ein=1000)
+    dn = scatt.DeviceNuclide(nuc, e_bins, params)
+    assert_parity(dn.elastic(v["freegas_Ein"]), v["freegas_elastic"], what="golden free gas")
+    dn.clear()
+    e_bins = synth.group_structure(70)
+    for mode, kw in (("skewed", {}), ("cont", {"elastic": "incoherent"})):
+        sab = synth.c4_sab(mode, **kw)
+        got = scatt.DeviceSab(sab).calc(e_bins, ace.SCATT_TYPE_LEGENDRE, 5, v[f"sab_{mode}_Ein"])
+        assert_parity(got[:-1], v[f"sab_{mode}"][:-1], what=f"golden S(a,b) {mode}")
+    integ, _ = scatt.default_context().test_legendre(8, *v["leaf_args"])
+    assert np.array_equal(integ, v["leaf_integrals"])

@@ -252,3 +252,52 @@ def test_g8_c1_fixture_structure_and_sanity(oracle):
     inel, nu = rn.inelastic(np.array([2.5]))
     assert np.allclose(inel[0], d + d3, atol=1e-15)
     assert np.allclose(nu[0], d + 2.0 * d3, atol=1e-15)
+
+
+# ---- committed fixtures (tests/golden/, written by scripts/make_golden.py) ------------------------
+def _gold():
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return json.load(open(os.path.join(d, "reference_kats.json"))), np.load(os.path.join(d, "oracle_vectors.npz"))
+
+
+def test_golden_reference_kats_file(oracle):
+    """The transcribed reference vectors, read from the fixture file rather than from this module."""
+    kats, _ = _gold()
+    k = kats["G4_mu_bounds_tolab"]
+    for Ein, Eg, ref in k["cases"]:
+        awr = 0.999167
+        w = (Eg * (1.0 + awr) ** 2 - Ein * (1.0 + awr * awr)) * (0.5 / (awr * Ein))
+        assert abs(oracle.lib().ref_tolab(awr, w) - ref) < 1e-15
+    got = oracle.calc_int_pn_tablelin(6, -1.0, -0.75, 0.0, 0.125)
+    assert np.allclose(got, kats["G5_int_pn_tablelin"]["values"], atol=1e-14)
+    rc, INTT, Eo, pdf, cdf, distro = oracle.convert_file6(2, mu5(oracle), 44, _law44_data(1.0), 2)
+    assert np.all(np.abs(distro[:, 0] - np.array(kats["G2_convert_file6_law44"]["R1_A1"])) < TEST_TOL)
+    assert np.all(np.abs(distro[:, 1] - np.array(kats["G2_convert_file6_law44"]["R0_A0p5"])) < TEST_TOL)
+
+
+def test_golden_oracle_vectors_reproduce(oracle):
+    """The oracle still produces the committed vectors bit for bit (same machine arithmetic: IEEE
+    double, no FMA contraction; the one libm-dependent path, Law 44, is compared to 1e-13)."""
+    from ndpp_b200 import egrid
+    from tests.util import small_heavy
+    _, v = _gold()
+    nuc, e_bins, params = synth.c1_fixture()
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    assert np.array_equal(rn.elastic(v["c1_Ein"]), v["c1_elastic"])
+    gi, gn = rn.inelastic(v["c1_Ein"])
+    assert np.allclose(gi, v["c1_inelastic"], rtol=0, atol=1e-13) and np.allclose(gn, v["c1_nu_inelastic"], rtol=0, atol=1e-13)
+    rn.close()
+    nuc = small_heavy()
+    rn = oracle.RefNuclide(nuc, synth.group_structure(70), ace.Params(order=7))
+    rn.convert_distro()
+    assert np.array_equal(rn.elastic(v["heavy_Eel"][:6]), v["heavy_elastic"][:6])
+    assert np.allclose(rn.inelastic(v["heavy_Ein"][-2:])[0], v["heavy_inelastic"][-2:], rtol=0, atol=1e-13)
+    rn.close()
+    sab = synth.c4_sab("skewed")
+    assert np.array_equal(oracle.sab_calc(sab, synth.group_structure(70), 5, v["sab_skewed_Ein"]), v["sab_skewed"])
+    a = v["leaf_args"]
+    got = np.stack([oracle.calc_int_pn_tablelin(8, *x) for x in zip(*a)])
+    assert np.array_equal(got, v["leaf_integrals"])
