@@ -27,8 +27,19 @@ struct SabDev {
     const double* el_e_in; const double* el_P; const double* el_mu;
 };
 
-__global__ void k_sab_el(SabDev sab, const double* __restrict__ e_bins, int nbins, int L, const double* __restrict__ Ein,
-                         int NE, double* __restrict__ out)
+// Angular basis of the output: P_l(mu) (LEGENDRE, the reference) or the indicator of the l-th of L equal-width
+// cosine bins on [-1, 1] (TABULAR; the reference leaves it unimplemented, src/scatt.F90:579-588, so the
+// semantics are this project's, DESIGN.md: element (b, g, E_in) = probability of group g and cosine bin b).
+__device__ __forceinline__ double sab_basis(int tabular, int L, int l, double mu)
+{
+    if (!tabular) return sab_basis(tabular, L, l, mu);
+    int b = (int)((mu + 1.0) * 0.5 * (double)L);
+    b = b < 0 ? 0 : (b > L - 1 ? L - 1 : b);
+    return (b == l) ? 1.0 : 0.0;
+}
+
+__global__ void k_sab_el(SabDev sab, const double* __restrict__ e_bins, int nbins, int L, int tabular,
+                         const double* __restrict__ Ein, int NE, double* __restrict__ out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)NE * L) return;
@@ -51,13 +62,13 @@ __global__ void k_sab_el(SabDev sab, const double* __restrict__ e_bins, int nbin
     double v = 0.0;
     if (sab.n_el_mu == 0) {
         const double mu = 1.0 - sab.el_e_in[isab] / E;
-        v = v + calc_pn(l, mu);
+        v = v + sab_basis(tabular, L, l, mu);
     } else if (sab.elastic_mode == SAB_ELASTIC_DISCRETE) {
         const double wgt = 1.0 / (double)sab.n_el_mu;
         for (int imu = 0; imu < sab.n_el_mu; ++imu) {
             const double mu = (1.0 - f) * sab.el_mu[(size_t)isab * sab.n_el_mu + imu] +
                               f * sab.el_mu[(size_t)(isab + 1) * sab.n_el_mu + imu];
-            v = v + wgt * calc_pn(l, mu);
+            v = v + wgt * sab_basis(tabular, L, l, mu);
         }
     }
     col[g * L + l] = sig * v;
@@ -65,7 +76,7 @@ __global__ void k_sab_el(SabDev sab, const double* __restrict__ e_bins, int nbin
 
 // wgt[] (n_eout) is prepared on the host exactly as :167-186
 __global__ void k_sab_inel_disc(SabDev sab, const double* __restrict__ wgt, const double* __restrict__ e_bins, int nbins,
-                                int L, const double* __restrict__ Ein, int NE, double* __restrict__ out)
+                                int L, int tabular, const double* __restrict__ Ein, int NE, double* __restrict__ out)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)NE * L) return;
@@ -100,7 +111,7 @@ __global__ void k_sab_inel_disc(SabDev sab, const double* __restrict__ wgt, cons
         const double wv = wgt[iEout];
         for (int imu = 0; imu < nmu; ++imu) {
             const double mu = (1.0 - f) * m0[imu] + f * m1[imu];
-            cur = cur + calc_pn(l, mu) * wv;
+            cur = cur + sab_basis(tabular, L, l, mu) * wv;
         }
     }
     if (gcur >= 0) col[gcur * L + l] = cur;
@@ -108,7 +119,8 @@ __global__ void k_sab_inel_disc(SabDev sab, const double* __restrict__ wgt, cons
 }
 
 // stage 1: one thread per (table E_in row, group, l); distro[(i*G + g)*L + l]
-__global__ void k_sab_cont_table(SabDev sab, const double* __restrict__ e_bins, int nbins, int L, double* __restrict__ distro)
+__global__ void k_sab_cont_table(SabDev sab, const double* __restrict__ e_bins, int nbins, int L, int tabular,
+                                 double* __restrict__ distro)
 {
     const int G = nbins - 1, nmu = sab.n_mu;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +143,7 @@ __global__ void k_sab_cont_table(SabDev sab, const double* __restrict__ e_bins, 
         const double mult = f_lo * SPDF(k);
         for (int imu = 0; imu < nmu; ++imu) {
             const double mu = (1.0 - f_lo) * mu_arr[(size_t)k * nmu + imu] + f_lo * mu_arr[(size_t)(k + 1) * nmu + imu];
-            d = d + calc_pn(l, mu) * mult;
+            d = d + sab_basis(tabular, L, l, mu) * mult;
         }
         iE_lo = k + 1;
     }
@@ -145,7 +157,7 @@ __global__ void k_sab_cont_table(SabDev sab, const double* __restrict__ e_bins, 
             const double mult = f_hi * SPDF(k);
             for (int imu = 0; imu < nmu; ++imu) {
                 const double mu = (1.0 - f_hi) * mu_arr[(size_t)k * nmu + imu] + f_hi * mu_arr[(size_t)(k + 1) * nmu + imu];
-                d = d + calc_pn(l, mu) * mult;
+                d = d + sab_basis(tabular, L, l, mu) * mult;
             }
             iE_hi = k - 1;
         }
@@ -153,7 +165,7 @@ __global__ void k_sab_cont_table(SabDev sab, const double* __restrict__ e_bins, 
     if (zero) { distro[t] = 0.0; return; }
     for (int k = iE_lo; k <= iE_hi; ++k) {
         const double pk = SPDF(k);
-        for (int imu = 0; imu < nmu; ++imu) d = d + calc_pn(l, mu_arr[(size_t)k * nmu + imu]) * pk;
+        for (int imu = 0; imu < nmu; ++imu) d = d + sab_basis(tabular, L, l, mu_arr[(size_t)k * nmu + imu]) * pk;
     }
 #undef SPDF
     distro[t] = d / (double)nmu;
@@ -182,15 +194,19 @@ __global__ void k_sab_cont_interp(SabDev sab, const double* __restrict__ distro,
 }
 
 // combine: one warp per E_in.  The last column is overwritten afterwards by k_copy_last.
-__global__ void k_sab_combine(const double* __restrict__ el, const double* __restrict__ inel, int G, int L, int NE,
-                              double* __restrict__ out)
+__global__ void k_sab_combine(const double* __restrict__ el, const double* __restrict__ inel, int G, int L, int tabular,
+                              int NE, double* __restrict__ out)
 {
     const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= NE) return;
     const size_t o = (size_t)w * G * L;
     double norm = 0.0;
-    for (int g = 0; g < G; ++g) norm = norm + (el[o + g * L] + inel[o + g * L]);
+    if (tabular) {  // total probability = sum over groups and cosine bins
+        for (int e = 0; e < G * L; ++e) norm = norm + (el[o + e] + inel[o + e]);
+    } else {
+        for (int g = 0; g < G; ++g) norm = norm + (el[o + g * L] + inel[o + g * L]);
+    }
     const bool pos = norm > 0.0;
     if (pos) norm = 1.0 / norm;
     for (int e = lane; e < G * L; e += 32) out[o + e] = pos ? (el[o + e] + inel[o + e]) * norm : 0.0;

@@ -709,7 +709,10 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
 {
     Ctx* c = s->ctx;
     if (NE <= 0) return 0;
-    const int G = n_bins - 1, L = order + 1, GL = G * L;
+    if (scatt_type != 0 && scatt_type != 1) return fail(c, "ndppgpu_sab: scatt_type must be 0 (Legendre) or 1 (tabular)");
+    const int tabular = scatt_type == 1;
+    const int G = n_bins - 1, L = tabular ? order : order + 1, GL = G * L;
+    if (L < 1) return fail(c, "ndppgpu_sab: scatt_order must give at least one moment / cosine bin");
     Timed tm(c, &c->pending_all);
     TmpBuf d_bins, el, inel, distro;
     if (tmp_upload(c, d_bins, e_bins, (size_t)n_bins)) return 1;
@@ -718,27 +721,27 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
     if (!p_inel) { if (tmp_alloc(c, inel, (size_t)NE * GL * sizeof(double))) return 1; p_inel = inel.as<double>(); }
     CK(c, cudaMemsetAsync(p_el, 0, (size_t)NE * GL * sizeof(double), c->stream));
     CK(c, cudaMemsetAsync(p_inel, 0, (size_t)NE * GL * sizeof(double), c->stream));
-    if (scatt_type == 0) {  // SCATT_TYPE_LEGENDRE; TABULAR is a TODO in the reference (src/scatt.F90:579-588)
+    {   // LEGENDRE as the reference; TABULAR (a TODO in the reference, src/scatt.F90:579-588) with this project's bins
         k_sab_el<<<blocks_for((long long)NE * L, 128), 128, 0, c->stream>>>(s->dev, d_bins.as<double>(), n_bins, L,
-                                                                            d_Ein, NE, p_el);
+                                                                            tabular, d_Ein, NE, p_el);
         if (launch_check(c, "k_sab_el")) return 1;
         if (s->dev.secondary_mode == SAB_SECONDARY_EQUAL || s->dev.secondary_mode == SAB_SECONDARY_SKEWED) {
             if (s->wgt_error)
                 return fail(c, "Number of Inelastic Outgoing Energies Less Than 4, but Skewed Weighting Requested by Data!");
             k_sab_inel_disc<<<blocks_for((long long)NE * L, 128), 128, 0, c->stream>>>(
-                s->dev, s->d_wgt.as<double>(), d_bins.as<double>(), n_bins, L, d_Ein, NE, p_inel);
+                s->dev, s->d_wgt.as<double>(), d_bins.as<double>(), n_bins, L, tabular, d_Ein, NE, p_inel);
             if (launch_check(c, "k_sab_inel_disc")) return 1;
         } else if (s->dev.secondary_mode == SAB_SECONDARY_CONT) {
             if (tmp_alloc(c, distro, (size_t)s->dev.n_in * GL * sizeof(double))) return 1;
             k_sab_cont_table<<<blocks_for((long long)s->dev.n_in * GL, 128), 128, 0, c->stream>>>(
-                s->dev, d_bins.as<double>(), n_bins, L, distro.as<double>());
+                s->dev, d_bins.as<double>(), n_bins, L, tabular, distro.as<double>());
             if (launch_check(c, "k_sab_cont_table")) return 1;
             k_sab_cont_interp<<<blocks_for((long long)NE * GL, 256), 256, 0, c->stream>>>(s->dev, distro.as<double>(),
                                                                                            GL, d_Ein, NE, p_inel);
             if (launch_check(c, "k_sab_cont_interp")) return 1;
         }
     }
-    k_sab_combine<<<blocks_for((long long)NE * 32, 128), 128, 0, c->stream>>>(p_el, p_inel, G, L, NE, d_out);
+    k_sab_combine<<<blocks_for((long long)NE * 32, 128), 128, 0, c->stream>>>(p_el, p_inel, G, L, tabular, NE, d_out);
     if (launch_check(c, "k_sab_combine")) return 1;
     k_copy_last<<<4, 256, 0, c->stream>>>(GL, NE, d_out);
     if (launch_check(c, "k_copy_last")) return 1;
@@ -848,6 +851,9 @@ int ndppgpu_nuclide_create(void* ctx, double awr, double kT, double freegas_cuto
     if (n_grid < 2 || n_bins < 2) return fail(c, "ndppgpu_nuclide_create: need at least 2 grid points and 1 group");
     if (params->mu_bins < 3) return fail(c, "ndppgpu_nuclide_create: mu_bins must be at least 3");
     const int L = (params->scatt_type == 0) ? params->order + 1 : params->order;
+    if (params->scatt_type != 0)   // integrate_distro: case (SCATT_TYPE_TABULAR) is empty (scattdata_header.F90:658-660, 1452-1460)
+        return fail(c, "ndppgpu_nuclide_create: tabular scattering of ACE nuclides is NOT YET IMPLEMENTED in the reference; "
+                       "only the S(a,b) path (ndppgpu_sab) has a tabular output");
     if (params->scatt_type == 0 && (params->order < 0 || L > NDPP_MAX_L))
         return fail(c, "ndppgpu_nuclide_create: scatt_order outside 0..MAX_LEGENDRE_ORDER (10)");
     if (params->ne_per_grp < 2) return fail(c, "ndppgpu_nuclide_create: ne_per_grp must be at least 2");
@@ -1212,7 +1218,7 @@ int ndppgpu_sab_dev(void* sab, const double* e_bins, int n_bins, int scatt_type,
 {
     Sab* s = (Sab*)sab;
     if (!s || !e_bins || !d_Ein || !d_scatt_mat) return fail(s ? s->ctx : nullptr, "ndppgpu_sab_dev: null argument");
-    if (order < 0 || order + 1 > NDPP_MAX_L) return fail(s->ctx, "ndppgpu_sab: scatt_order outside 0..10");
+    if (scatt_type == 0 && (order < 0 || order + 1 > NDPP_MAX_L)) return fail(s->ctx, "ndppgpu_sab: scatt_order outside 0..10");
     CK(s->ctx, cudaSetDevice(s->ctx->device));
     return sab_dev(s, e_bins, n_bins, scatt_type, order, d_Ein, NE, d_scatt_mat, nullptr, nullptr);
 }
@@ -1222,11 +1228,12 @@ int ndppgpu_sab(void* sab, const double* e_bins, int n_bins, int scatt_type, int
 {
     Sab* s = (Sab*)sab;
     if (!s || !e_bins || !Ein || !scatt_mat) return fail(s ? s->ctx : nullptr, "ndppgpu_sab: null argument");
-    if (order < 0 || order + 1 > NDPP_MAX_L) return fail(s->ctx, "ndppgpu_sab: scatt_order outside 0..10");
+    if (scatt_type == 0 && (order < 0 || order + 1 > NDPP_MAX_L)) return fail(s->ctx, "ndppgpu_sab: scatt_order outside 0..10");
+    if (scatt_type == 1 && order < 1) return fail(s->ctx, "ndppgpu_sab: tabular scattering needs at least one cosine bin");
     Ctx* c = s->ctx;
     CK(c, cudaSetDevice(c->device));
     if (NE <= 0) return 0;
-    const size_t nout = (size_t)NE * (n_bins - 1) * (order + 1);
+    const size_t nout = (size_t)NE * (n_bins - 1) * (scatt_type == 1 ? order : order + 1);
     DevBuf d_E, d_out, d_el, d_inel;
     if (upload(c, d_E, Ein, (size_t)NE) || dev_alloc(c, d_out, nout * sizeof(double)) ||
         dev_alloc(c, d_el, nout * sizeof(double)) || dev_alloc(c, d_inel, nout * sizeof(double)))

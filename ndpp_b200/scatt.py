@@ -191,7 +191,7 @@ class DeviceSab:
 
     def calc(self, energy_bins, scatt_type, order, E_grid, parts=False):
         eb, Ein = f64(energy_bins), f64(E_grid)
-        out = np.empty((len(Ein), len(eb) - 1, order + 1))
+        out = np.empty((len(Ein), len(eb) - 1, order + 1 if scatt_type == SCATT_TYPE_LEGENDRE else order))
         el = np.empty_like(out) if parts else None
         inel = np.empty_like(out) if parts else None
         check(self.lib.ndppgpu_sab(self.h, dp(eb), len(eb), scatt_type, order, dp(Ein), len(Ein), dp(out), dp(el),
@@ -217,7 +217,8 @@ class DeviceSab:
 
 def calc_scattsab(sab: SAlphaBeta, energy_bins, scatt_type: int, order: int, mu_bins: int, E_grid,
                   ctx: Optional[Context] = None) -> np.ndarray:
-    """calc_scattsab (src/scatt.F90:543-596): scatt_mat[NE][G][order+1].  E_grid comes from sab_egrid
+    """calc_scattsab (src/scatt.F90:543-596): scatt_mat[NE][G][order+1] (Legendre) or [NE][G][order] cosine bins
+    (tabular: a TODO in the reference, :579-588; semantics in DESIGN.md).  E_grid comes from sab_egrid
     (src/sab.F90:460), which stays on the host side of the seam.  mu_bins is accepted and unused, as
     in the reference."""
     ds = DeviceSab(sab, ctx)

@@ -134,6 +134,9 @@ void *ref_sab_create(double awr, double kT, double threshold_inelastic, double t
                      const double *elastic_P, const double *elastic_mu);
 int ref_sab_calc(void *sab, const double *e_bins, int n_bins, int order, const double *Ein, int NE, double *scatt_mat,
                  double *el_out, double *inel_out, int n_threads);
+/* TABULAR output (project-defined, parity unpinned): `order` equal-width cosine bins */
+int ref_sab_calc_tabular(void *sab, const double *e_bins, int n_bins, int order, const double *Ein, int NE,
+                         double *scatt_mat, double *el_out, double *inel_out, int n_threads);
 void ref_sab_free(void *sab);
 
 #ifdef __cplusplus

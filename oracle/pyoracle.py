@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.ref_sab_create.argtypes = [C.c_double] * 4 + [C.c_int] * 4 + [c_dp] * 4 + [c_ip] + [c_dp] * 3 + \
                                     [C.c_int] * 3 + [c_dp] * 3
         L.ref_sab_calc.argtypes = [C.c_void_p, c_dp, C.c_int, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp, C.c_int]
+        L.ref_sab_calc_tabular.argtypes = L.ref_sab_calc.argtypes
         L.ref_sab_free.argtypes = [C.c_void_p]
         L.ref_sab_free.restype = None
         L.ref_freegas_counters.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
@@ -299,8 +300,9 @@ class RefNuclide:
             pass
 
 
-def sab_calc(sab, e_bins, order, Ein, parts=False):
-    """calc_scattsab (src/scatt.F90:543-596) on an ndpp_b200.ace.SAlphaBeta; returns [iE][g][l]."""
+def sab_calc(sab, e_bins, order, Ein, parts=False, tabular=False):
+    """calc_scattsab (src/scatt.F90:543-596) on an ndpp_b200.ace.SAlphaBeta; returns [iE][g][l]
+    (tabular: `order` cosine bins, project-defined semantics, see sab_ref.c)."""
     from ndpp_b200.ace import SAB_SECONDARY_CONT
     L = lib()
     e_bins, Ein = f64(e_bins), f64(Ein)
@@ -323,9 +325,9 @@ def sab_calc(sab, e_bins, order, Ein, parts=False):
                          dp(cp), dp(cm), sab.elastic_mode, sab.n_elastic_e_in, sab.n_elastic_mu, dp(ee), dp(eP),
                          dp(em))
     G = len(e_bins) - 1
-    out = np.zeros((len(Ein), G, order + 1))
+    out = np.zeros((len(Ein), G, order if tabular else order + 1))
     el, inel = np.zeros_like(out), np.zeros_like(out)
-    L.ref_sab_calc(h, dp(e_bins), len(e_bins), order, dp(Ein), len(Ein), dp(out), dp(el), dp(inel), 1)
+    (L.ref_sab_calc_tabular if tabular else L.ref_sab_calc)(h, dp(e_bins), len(e_bins), order, dp(Ein), len(Ein), dp(out), dp(el), dp(inel), 1)
     L.ref_sab_free(h)
     check_errors()
     return (out, el, inel) if parts else out

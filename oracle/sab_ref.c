@@ -104,13 +104,30 @@ void ref_sab_free(void *h)
     free(s);
 }
 
+/* Angular basis of the output.  LEGENDRE: P_l(mu), l = 0..order (the reference).  TABULAR: the reference has
+ * no implementation (calc_scattsab: "TODO", src/scatt.F90:579-588; scattdata_header.F90:658-660), so the
+ * semantics are this project's: `order` equal-width cosine bins on [-1, 1]; a discrete cosine
+ * deposits its weight in the bin that contains it (mu = 1 in the last bin), so that element (b, g, E_in) is the
+ * probability of scattering into group g and cosine bin b.  Parity for this mode is unpinned. */
+static int g_sab_tabular = 0;
+static int sab_orders(int order) { return g_sab_tabular ? order : order + 1; }
+static double sab_basis(int L, int l, double mu)
+{
+    int b;
+    if (!g_sab_tabular) return ref_calc_pn(l, mu);
+    b = (int)((mu + ONE) * 0.5 * (double)L);
+    if (b < 0) b = 0;
+    if (b > L - 1) b = L - 1;
+    return (b == l) ? ONE : ZERO;
+}
+
 #define SI(l, g, iE) sab_int[((l)-1) + (size_t)L * (((g)-1) + (size_t)groups * ((iE)-1))]
 
 /* src/sab.F90:21-109 */
 static void integrate_sab_el(const ref_sab *sab, const double *ein_grid, int NE, const double *e_bins, int nbins,
                              int order, double *sab_int)
 {
-    int L = order + 1, groups = nbins - 1, iEin, g, imu, l, isab;
+    int L = sab_orders(order), groups = nbins - 1, iEin, g, imu, l, isab;
     double sig = ZERO, mu, Ein, f, wgt = ZERO;
 
     memset(sab_int, 0, sizeof(double) * (size_t)L * groups * NE);
@@ -141,12 +158,12 @@ static void integrate_sab_el(const ref_sab *sab, const double *ein_grid, int NE,
 
         if (sab->n_elastic_mu == 0) {
             mu = ONE - A1(sab->elastic_e_in, isab) / Ein;
-            for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + ref_calc_pn(l - 1, mu);
+            for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + sab_basis(L, l - 1, mu);
         } else if (sab->elastic_mode == REF_SAB_ELASTIC_DISCRETE) {
             for (imu = 1; imu <= sab->n_elastic_mu; ++imu) {
                 mu = (ONE - f) * sab->elastic_mu[(size_t)(isab - 1) * sab->n_elastic_mu + (imu - 1)] +
                      f * sab->elastic_mu[(size_t)isab * sab->n_elastic_mu + (imu - 1)];
-                for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + wgt * ref_calc_pn(l - 1, mu);
+                for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + wgt * sab_basis(L, l - 1, mu);
             }
         }
         for (g = 1; g <= groups; ++g)
@@ -158,7 +175,7 @@ static void integrate_sab_el(const ref_sab *sab, const double *ein_grid, int NE,
 static void integrate_sab_inel_disc(const ref_sab *sab, const double *ein_grid, int NE, const double *e_bins,
                                     int nbins, int order, double *sab_int)
 {
-    int L = order + 1, groups = nbins - 1, iEin, iEout, g, imu, l, isab, NEo = sab->n_inelastic_e_out,
+    int L = sab_orders(order), groups = nbins - 1, iEin, iEout, g, imu, l, isab, NEo = sab->n_inelastic_e_out,
         nmu = sab->n_inelastic_mu;
     double sig, mu, Ein, Eout, f, s;
     double *wgt = (double *)malloc(sizeof(double) * (NEo > 0 ? NEo : 1));
@@ -213,7 +230,7 @@ static void integrate_sab_inel_disc(const ref_sab *sab, const double *ein_grid, 
             for (imu = 1; imu <= nmu; ++imu) {
                 mu = (ONE - f) * sab->inelastic_mu[((size_t)(isab - 1) * NEo + (iEout - 1)) * nmu + (imu - 1)] +
                      f * sab->inelastic_mu[((size_t)isab * NEo + (iEout - 1)) * nmu + (imu - 1)];
-                for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + ref_calc_pn(l - 1, mu) * A1(wgt, iEout);
+                for (l = 1; l <= L; ++l) SI(l, g, iEin) = SI(l, g, iEin) + sab_basis(L, l - 1, mu) * A1(wgt, iEout);
             }
         }
         for (g = 1; g <= groups; ++g)
@@ -226,7 +243,7 @@ static void integrate_sab_inel_disc(const ref_sab *sab, const double *ein_grid, 
 static void integrate_sab_inel_cont(const ref_sab *sab, const double *ein_grid, int NE, const double *e_bins,
                                     int nbins, int order, double *sab_int)
 {
-    int L = order + 1, groups = nbins - 1, iEin, g, imu, l, isab, iE, iE_lo, iE_hi, NEout, nmu = sab->n_inelastic_mu,
+    int L = sab_orders(order), groups = nbins - 1, iEin, g, imu, l, isab, iE, iE_lo, iE_hi, NEout, nmu = sab->n_inelastic_mu,
         NEi = sab->n_inelastic_e_in;
     double sig, mu, Ein, f, f_lo, f_hi, mult;
     double *distro = (double *)calloc((size_t)L * groups * NEi, sizeof(double));
@@ -258,7 +275,7 @@ static void integrate_sab_inel_cont(const ref_sab *sab, const double *ein_grid, 
                 mult = f_lo * A1(pdf, iE_lo);
                 for (imu = 1; imu <= nmu; ++imu) {
                     mu = (ONE - f_lo) * MU(imu, iE_lo) + f_lo * MU(imu, iE_lo + 1);
-                    for (l = 1; l <= L; ++l) DI(l, g, iEin) = DI(l, g, iEin) + ref_calc_pn(l - 1, mu) * mult;
+                    for (l = 1; l <= L; ++l) DI(l, g, iEin) = DI(l, g, iEin) + sab_basis(L, l - 1, mu) * mult;
                 }
                 iE_lo = iE_lo + 1;
             }
@@ -273,14 +290,14 @@ static void integrate_sab_inel_cont(const ref_sab *sab, const double *ein_grid, 
                 mult = f_hi * A1(pdf, iE_hi);
                 for (imu = 1; imu <= nmu; ++imu) {
                     mu = (ONE - f_hi) * MU(imu, iE_hi) + f_hi * MU(imu, iE_hi + 1);
-                    for (l = 1; l <= L; ++l) DI(l, g, iEin) = DI(l, g, iEin) + ref_calc_pn(l - 1, mu) * mult;
+                    for (l = 1; l <= L; ++l) DI(l, g, iEin) = DI(l, g, iEin) + sab_basis(L, l - 1, mu) * mult;
                 }
                 iE_hi = iE_hi - 1;
             }
             for (iE = iE_lo; iE <= iE_hi; ++iE) {
                 for (imu = 1; imu <= nmu; ++imu)
                     for (l = 1; l <= L; ++l)
-                        DI(l, g, iEin) = DI(l, g, iEin) + ref_calc_pn(l - 1, MU(imu, iE)) * A1(pdf, iE);
+                        DI(l, g, iEin) = DI(l, g, iEin) + sab_basis(L, l - 1, MU(imu, iE)) * A1(pdf, iE);
             }
             for (l = 1; l <= L; ++l) DI(l, g, iEin) = DI(l, g, iEin) / (double)nmu;
         }
@@ -318,7 +335,7 @@ int ref_sab_calc(void *h, const double *e_bins, int n_bins, int order, const dou
                  double *el_out, double *inel_out, int n_threads)
 {
     const ref_sab *sab = (const ref_sab *)h;
-    int L = order + 1, groups = n_bins - 1, iE, g, l;
+    int L = sab_orders(order), groups = n_bins - 1, iE, g, l;
     size_t n = (size_t)L * groups * NE;
     double *el = (double *)malloc(sizeof(double) * n), *inel = (double *)malloc(sizeof(double) * n);
     double norm_sum;
@@ -341,7 +358,12 @@ int ref_sab_calc(void *h, const double *e_bins, int n_bins, int order, const dou
                 sab_int[k] = el[k] + inel[k];
             }
         norm_sum = ZERO;
-        for (g = 1; g <= groups; ++g) norm_sum = norm_sum + SI(1, g, iE);
+        if (g_sab_tabular) {   /* total probability = sum over groups and cosine bins */
+            for (g = 1; g <= groups; ++g)
+                for (l = 1; l <= L; ++l) norm_sum = norm_sum + SI(l, g, iE);
+        } else {
+            for (g = 1; g <= groups; ++g) norm_sum = norm_sum + SI(1, g, iE);
+        }
         if (norm_sum > ZERO) {
             norm_sum = ONE / norm_sum;
             for (g = 1; g <= groups; ++g)
@@ -360,4 +382,15 @@ int ref_sab_calc(void *h, const double *e_bins, int n_bins, int order, const dou
     free(el);
     free(inel);
     return ref_error_count();
+}
+
+/* scatt_type = SCATT_TYPE_TABULAR (1): `order` cosine bins; scatt_mat is (order, groups, NE). */
+int ref_sab_calc_tabular(void *h, const double *e_bins, int n_bins, int order, const double *Ein, int NE,
+                         double *scatt_mat, double *el_out, double *inel_out, int n_threads)
+{
+    int rc;
+    g_sab_tabular = 1;
+    rc = ref_sab_calc(h, e_bins, n_bins, order, Ein, NE, scatt_mat, el_out, inel_out, n_threads);
+    g_sab_tabular = 0;
+    return rc;
 }

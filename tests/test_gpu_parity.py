@@ -362,3 +362,24 @@ def test_against_committed_golden_vectors(scatt):
         assert_parity(got[:-1], v[f"sab_{mode}"][:-1], what=f"golden S(a,b) {mode}")
     integ, _ = scatt.default_context().test_legendre(8, *v["leaf_args"])
     assert np.array_equal(integ, v["leaf_integrals"])
+
+
+@pytest.mark.parametrize("mode,kw", [("skewed", {}), ("equal", {"elastic": "coherent"}), ("cont", {"elastic": "incoherent"})])
+def test_c4_sab_tabular_histogram(scatt, oracle, mode, kw):
+    """C4's 16-bin cosine histogram (scatt_type = TABULAR; semantics defined by this project because
+    the reference leaves it unimplemented, parity unpinned): CUDA vs the oracle, and the bins of a group
+    sum to the group's P0 of the Legendre output."""
+    from ndpp_b200 import egrid
+    sab = synth.c4_sab(mode, **kw)
+    e_bins = synth.group_structure(70)
+    E = egrid.sab_egrid(sab, e_bins)
+    ds = scatt.DeviceSab(sab)
+    got = ds.calc(e_bins, ace.SCATT_TYPE_TABULAR, 16, E)
+    leg = ds.calc(e_bins, ace.SCATT_TYPE_LEGENDRE, 5, E)
+    assert got.shape == (len(E), 70, 16)
+    assert np.allclose(got.sum(axis=2), leg[:, :, 0], atol=1e-13)
+    idx = np.unique(np.concatenate([np.arange(0, len(E), 23), [len(E) - 2, len(E) - 1]]))
+    ref = oracle.sab_calc(sab, e_bins, 16, E[idx], tabular=True)
+    assert_parity(got[idx][:-1], ref[:-1], what=f"S(a,b) histogram {mode}")
+    with pytest.raises(Exception):
+        scatt.DeviceNuclide(small_heavy(), e_bins, ace.Params(order=16, scatt_type=ace.SCATT_TYPE_TABULAR))

@@ -301,3 +301,25 @@ def test_golden_oracle_vectors_reproduce(oracle):
     a = v["leaf_args"]
     got = np.stack([oracle.calc_int_pn_tablelin(8, *x) for x in zip(*a)])
     assert np.array_equal(got, v["leaf_integrals"])
+
+
+# ---- row H: tabular (histogram) S(a,b) output -- project-defined, no reference implementation ------
+@pytest.mark.parametrize("mode,kw", [("skewed", {}), ("equal", {"elastic": "coherent"}), ("cont", {"elastic": "incoherent"})])
+def test_sab_tabular_properties(oracle, mode, kw):
+    """16 cosine bins: every column sums to 1 over (group, bin); summing the bins of a group gives
+    the group's P0 of the Legendre output; a single bin reproduces P0 exactly."""
+    from ndpp_b200 import egrid
+    sab = synth.c4_sab(mode, **kw)
+    e_bins = synth.group_structure(70)
+    E = egrid.sab_egrid(sab, e_bins)[::97]
+    h = oracle.sab_calc(sab, e_bins, 16, E, tabular=True)
+    leg = oracle.sab_calc(sab, e_bins, 5, E)
+    assert h.shape == (len(E), 70, 16) and np.all(h >= 0.0)
+    live = leg[:, :, 0].sum(axis=1) > 0
+    assert np.allclose(h.sum(axis=(1, 2))[live], 1.0, atol=1e-13)
+    assert np.allclose(h.sum(axis=2), leg[:, :, 0], atol=1e-13)
+    one = oracle.sab_calc(sab, e_bins, 1, E, tabular=True)
+    assert np.allclose(one[:, :, 0], leg[:, :, 0], atol=1e-13)
+    # mean cosine from the histogram (bin centres) agrees with P1 to within half a bin width
+    centres = -1.0 + (np.arange(16) + 0.5) / 8.0
+    assert np.all(np.abs((h * centres).sum(axis=(1, 2)) - leg[:, :, 1].sum(axis=1))[live] <= 1.0 / 16.0 + 1e-12)
