@@ -149,6 +149,28 @@ int ndppgpu_sab_free(void *sab);
 
 /* ---- leaf check of the device Legendre helpers: integrals[n][L] = calc_int_pn_tablelin(L, xlow, xhigh,
  *      flow, fhigh) (src/legendre.F90:22) and pn[n][L] = calc_pn(l, xlow) (:349) for n inputs ------- */
+/* ---- the two steps that follow the integrator in the reference's driver (src/ndpp.F90:611-648) ----
+ *
+ * ndppgpu_apply_tol  replaces apply_tol_scatt(data, tol) (src/scatt.F90:786-818): groups whose P0 lies in
+ *                    (0, tol) are zeroed for every order and the column is renormalised to its original
+ *                    sum of P0.  mat is [NE][G][L] (Fortran data(L, G, NE)), modified in place.
+ * ndppgpu_thin_grid  replaces thin_grid(xout, yout, tokeep, tol, compression, maxerr [, yout2])
+ *                    (src/thin.F90:19-47): greedy thinning of the E_in grid with log-x interpolation; x, y1
+ *                    and (if not NULL) y2 are compacted in place to the *n_kept points kept, as the Fortran
+ *                    re-allocates its arrays.  compression is the reference's; max_abs_err is the plain
+ *                    maximum of |interpolated - y| over the accepted tests (the reference's maxerr mixes a
+ *                    relative comparison with an absolute store, src/thin.F90:127-131, and is not reproduced).
+ * The *_dev forms take device pointers (d_keep: NE ints of scratch receiving the kept indices) so that the
+ * tolerance and the thinning can run before the moment arrays are gathered or copied to the host. */
+int ndppgpu_apply_tol(void *ctx, double *mat, int NE, int G, int L, double tol);
+int ndppgpu_apply_tol_dev(void *ctx, double *d_mat, int NE, int G, int L, double tol);
+int ndppgpu_thin_grid(void *ctx, double *x, double *y1, double *y2, int NE, int GL, const double *tokeep, int n_tokeep,
+                      double tol, int *n_kept, double *compression, double *max_abs_err);
+int ndppgpu_thin_grid_dev(void *ctx, const double *d_x, const double *d_y1, const double *d_y2, int NE, int GL,
+                          const double *tokeep, int n_tokeep, double tol, int *d_keep, int *n_kept, double *compression,
+                          double *max_abs_err);
+int ndppgpu_gather_columns_dev(void *ctx, const double *d_src, const int *d_keep, int n_kept, int width, double *d_dst);
+
 /* Self-test of the shared-reciprocal division (csrc/legendre.cuh: FastDiv) against the IEEE operator on
  * per_thread random operand pairs per GPU thread.  counts2 = {pairs, mismatches}; mismatches must be zero. */
 int ndppgpu_test_exact_math(void *ctx, unsigned long long seed, int per_thread, unsigned long long *counts2);

@@ -24,7 +24,8 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_nuclide_n_slots", "ndppgpu_nuclide_slot_info", "ndppgpu_nuclide_slot_row_np",
            "ndppgpu_nuclide_get_table", "ndppgpu_nuclide_free", "ndppgpu_sab_create", "ndppgpu_sab", "ndppgpu_sab_dev",
            "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
-           "ndppgpu_test_exact_math"]
+           "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
+           "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev"]
 
 
 class NdppGpuError(RuntimeError):
@@ -88,6 +89,11 @@ def load() -> C.CDLL:
     L.ndppgpu_nuclide_set_table.argtypes = [vp, i, i, c_dp]
     L.ndppgpu_test_legendre.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     L.ndppgpu_test_exact_math.argtypes = [vp, C.c_ulonglong, i, C.POINTER(C.c_ulonglong)]
+    L.ndppgpu_apply_tol.argtypes = [vp, c_dp, i, i, i, d]
+    L.ndppgpu_apply_tol_dev.argtypes = [vp, vp, i, i, i, d]
+    L.ndppgpu_thin_grid.argtypes = [vp, c_dp, c_dp, c_dp, i, i, c_dp, i, d, c_ip, c_dp, c_dp]
+    L.ndppgpu_thin_grid_dev.argtypes = [vp, vp, vp, vp, i, i, c_dp, i, d, vp, c_ip, c_dp, c_dp]
+    L.ndppgpu_gather_columns_dev.argtypes = [vp, vp, vp, i, i, vp]
     _lib = L
     return L
 

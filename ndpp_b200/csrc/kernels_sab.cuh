@@ -32,7 +32,7 @@ struct SabDev {
 // semantics are this project's, DESIGN.md: element (b, g, E_in) = probability of group g and cosine bin b).
 __device__ __forceinline__ double sab_basis(int tabular, int L, int l, double mu)
 {
-    if (!tabular) return sab_basis(tabular, L, l, mu);
+    if (!tabular) return calc_pn(l, mu);
     int b = (int)((mu + 1.0) * 0.5 * (double)L);
     b = b < 0 ? 0 : (b > L - 1 ? L - 1 : b);
     return (b == l) ? 1.0 : 0.0;

@@ -23,6 +23,7 @@
 #include "kernels_file6.cuh"
 #include "kernels_file6_ws.cuh"
 #include "kernels_freegas.cuh"
+#include "kernels_post.cuh"
 #include "kernels_sab.cuh"
 
 using namespace ndpp;
@@ -1132,6 +1133,109 @@ int ndppgpu_test_exact_math(void* ctx, unsigned long long seed, int per_thread, 
     if (launch_check(c, "k_test_exact_math")) return 1;
     CK(c, cudaMemcpyAsync(counts2, d.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- the steps after the integrator: apply_tol_scatt (src/scatt.F90:786-818), thin_grid (src/thin.F90) ----
+int ndppgpu_apply_tol_dev(void* ctx, double* d_mat, int NE, int G, int L, double tol)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !d_mat) return fail(c, "ndppgpu_apply_tol_dev: null argument");
+    if (NE <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    Timed tm(c, &c->pending_all);
+    k_apply_tol<<<blocks_for((long long)NE * 32, 128), 128, 0, c->stream>>>(d_mat, NE, G, L, tol);
+    return launch_check(c, "k_apply_tol");
+}
+
+int ndppgpu_apply_tol(void* ctx, double* mat, int NE, int G, int L, double tol)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !mat) return fail(c, "ndppgpu_apply_tol: null argument");
+    if (NE <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)NE * G * L;
+    TmpBuf d;
+    if (tmp_upload(c, d, mat, n)) return 1;
+    if (ndppgpu_apply_tol_dev(ctx, d.as<double>(), NE, G, L, tol)) return 1;
+    CK(c, cudaMemcpyAsync(mat, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (double)(n * sizeof(double));
+    return 0;
+}
+
+int ndppgpu_thin_grid_dev(void* ctx, const double* d_x, const double* d_y1, const double* d_y2, int NE, int GL,
+                          const double* tokeep, int n_tokeep, double tol, int* d_keep, int* n_kept, double* compression,
+                          double* max_abs_err)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !d_x || !d_y1 || !d_keep || !n_kept) return fail(c, "ndppgpu_thin_grid_dev: null argument");
+    CK(c, cudaSetDevice(c->device));
+    *n_kept = 0;
+    if (compression) *compression = 0.0;
+    if (max_abs_err) *max_abs_err = 0.0;
+    if (NE <= 0) return 0;
+    TmpBuf d_tk, d_out, d_max;
+    if (tmp_upload(c, d_tk, tokeep, (size_t)std::max(n_tokeep, 0)) || tmp_alloc(c, d_out, sizeof(int)) ||
+        tmp_alloc(c, d_max, sizeof(double)))
+        return 1;
+    {
+        Timed tm(c, &c->pending_all);
+        k_thin_grid<<<1, THIN_WARPS * 32, 0, c->stream>>>(d_x, d_y1, d_y2, NE, GL, d_tk.as<double>(), std::max(n_tokeep, 0),
+                                                          tol, d_keep, d_out.as<int>(), d_max.as<double>());
+        if (launch_check(c, "k_thin_grid")) return 1;
+    }
+    double m = 0.0;
+    CK(c, cudaMemcpyAsync(n_kept, d_out.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&m, d_max.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));   // tokeep is caller-owned pageable memory
+    if (compression) *compression = ((double)NE - (double)*n_kept) / (double)NE;
+    if (max_abs_err) *max_abs_err = m;
+    return 0;
+}
+
+int ndppgpu_gather_columns_dev(void* ctx, const double* d_src, const int* d_keep, int n_kept, int width, double* d_dst)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !d_src || !d_keep || !d_dst) return fail(c, "ndppgpu_gather_columns_dev: null argument");
+    if (n_kept <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    TmpBuf d_n;
+    if (tmp_upload(c, d_n, &n_kept, 1)) return 1;
+    k_gather_cols<<<std::min(n_kept, 4 * c->sm_count), 128, 0, c->stream>>>(d_src, d_keep, d_n.as<int>(), width, d_dst);
+    if (launch_check(c, "k_gather_cols")) return 1;
+    CK(c, cudaStreamSynchronize(c->stream));   // n_kept lives on the caller's stack
+    return 0;
+}
+
+int ndppgpu_thin_grid(void* ctx, double* x, double* y1, double* y2, int NE, int GL, const double* tokeep, int n_tokeep,
+                      double tol, int* n_kept, double* compression, double* max_abs_err)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !x || !y1 || !n_kept) return fail(c, "ndppgpu_thin_grid: null argument");
+    *n_kept = 0;
+    if (NE <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)NE * GL;
+    TmpBuf dx, d1, d2, dk, o1, o2, ox;
+    if (tmp_upload(c, dx, x, (size_t)NE) || tmp_upload(c, d1, y1, n) || tmp_alloc(c, dk, (size_t)NE * sizeof(int))) return 1;
+    if (y2 && tmp_upload(c, d2, y2, n)) return 1;
+    if (ndppgpu_thin_grid_dev(ctx, dx.as<double>(), d1.as<double>(), y2 ? d2.as<double>() : nullptr, NE, GL, tokeep, n_tokeep,
+                              tol, dk.as<int>(), n_kept, compression, max_abs_err))
+        return 1;
+    const size_t m = (size_t)*n_kept * GL;
+    if (tmp_alloc(c, o1, m * sizeof(double)) || tmp_alloc(c, ox, (size_t)*n_kept * sizeof(double))) return 1;
+    if (ndppgpu_gather_columns_dev(ctx, d1.as<double>(), dk.as<int>(), *n_kept, GL, o1.as<double>())) return 1;
+    if (ndppgpu_gather_columns_dev(ctx, dx.as<double>(), dk.as<int>(), *n_kept, 1, ox.as<double>())) return 1;
+    CK(c, cudaMemcpyAsync(y1, o1.p, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(x, ox.p, (size_t)*n_kept * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (y2) {
+        if (tmp_alloc(c, o2, m * sizeof(double))) return 1;
+        if (ndppgpu_gather_columns_dev(ctx, d2.as<double>(), dk.as<int>(), *n_kept, GL, o2.as<double>())) return 1;
+        CK(c, cudaMemcpyAsync(y2, o2.p, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (double)((y2 ? 2 : 1) * m * sizeof(double));
     return 0;
 }
 

@@ -226,3 +226,36 @@ def calc_scattsab(sab: SAlphaBeta, energy_bins, scatt_type: int, order: int, mu_
         return ds.calc(energy_bins, scatt_type, order, E_grid)
     finally:
         ds.clear()
+
+
+# ---- the steps that follow the integrator in the reference's driver (src/ndpp.F90:611-648) --------
+def apply_tol_scatt(data: np.ndarray, tol: float, ctx: Optional[Context] = None) -> np.ndarray:
+    """apply_tol_scatt(data, tol) (src/scatt.F90:786-818) on [NE][G][L], in place like the Fortran."""
+    ctx = ctx or default_context()
+    assert data.dtype == np.float64 and data.flags.c_contiguous and data.ndim == 3
+    NE, G, L = data.shape
+    check(ctx.lib.ndppgpu_apply_tol(ctx.h, dp(data), NE, G, L, float(tol)), ctx.h)
+    return data
+
+
+def thin_grid(xout: np.ndarray, yout: np.ndarray, tokeep, tol: float, yout2: Optional[np.ndarray] = None,
+              ctx: Optional[Context] = None):
+    """thin_grid(xout, yout, tokeep, tol, compression, maxerr [, yout2]) (src/thin.F90:19-47).  Returns
+    (xout, yout, yout2, compression, max_abs_err) with the arrays cut to the points kept (the Fortran
+    re-allocates them).  max_abs_err is the plain max |interpolated - y| (include/ndppgpu.h)."""
+    ctx = ctx or default_context()
+    x = np.array(xout, dtype=np.float64, order="C", copy=True)
+    y = np.array(yout, dtype=np.float64, order="C", copy=True)
+    y2 = np.array(yout2, dtype=np.float64, order="C", copy=True) if yout2 is not None else None
+    NE = len(x)
+    GL = y.size // max(NE, 1)
+    tk = f64(tokeep)
+    n = C.c_int(0)
+    comp, merr = C.c_double(0.0), C.c_double(0.0)
+    check(ctx.lib.ndppgpu_thin_grid(ctx.h, dp(x), dp(y), dp(y2), NE, GL, dp(tk), len(tk), float(tol), C.byref(n),
+                                    C.byref(comp), C.byref(merr)), ctx.h)
+    k = n.value
+    y = y.reshape(NE, -1)[:k].reshape((k,) + yout.shape[1:])
+    if y2 is not None:
+        y2 = y2.reshape(NE, -1)[:k].reshape((k,) + yout2.shape[1:])
+    return x[:k], y, y2, comp.value, merr.value

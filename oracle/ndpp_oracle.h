@@ -139,6 +139,11 @@ int ref_sab_calc_tabular(void *sab, const double *e_bins, int n_bins, int order,
                          double *scatt_mat, double *el_out, double *inel_out, int n_threads);
 void ref_sab_free(void *sab);
 
+/* ---- the two steps after the integrator: apply_tol_scatt (src/scatt.F90:786-818), thin_grid (src/thin.F90) ---- */
+void ref_apply_tol_scatt(double *data, int L, int G, int NE, double tol);
+int ref_thin_grid(const double *x, const double *y1, const double *y2, int NE, int GL, const double *tokeep, int n_tokeep,
+                  double tol, int *keep, double *compression, double *maxerr, double *max_abs);
+
 #ifdef __cplusplus
 }
 #endif

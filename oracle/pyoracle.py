@@ -75,6 +75,9 @@ def lib() -> C.CDLL:
         L.ref_sab_calc_tabular.argtypes = L.ref_sab_calc.argtypes
         L.ref_sab_free.argtypes = [C.c_void_p]
         L.ref_sab_free.restype = None
+        L.ref_apply_tol_scatt.argtypes = [c_dp, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.ref_apply_tol_scatt.restype = None
+        L.ref_thin_grid.argtypes = [c_dp, c_dp, c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_double, c_ip, c_dp, c_dp, c_dp]
         L.ref_freegas_counters.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
         L.ref_freegas_counters.restype = None
         _lib = L
@@ -331,3 +334,26 @@ def sab_calc(sab, e_bins, order, Ein, parts=False, tabular=False):
     L.ref_sab_free(h)
     check_errors()
     return (out, el, inel) if parts else out
+
+
+def apply_tol_scatt(data, tol):
+    """apply_tol_scatt (src/scatt.F90:786-818) on [iE][g][l]; returns a new array."""
+    d = np.array(data, dtype=np.float64, order="C", copy=True)
+    NE, G, Lm = d.shape
+    lib().ref_apply_tol_scatt(dp(d), Lm, G, NE, float(tol))
+    return d
+
+
+def thin_grid(x, y, tokeep, tol, y2=None):
+    """thin_grid (src/thin.F90): returns (kept indices, compression, maxerr as the reference computes it,
+    plain max |interpolated - y|)."""
+    x, y = f64(x), f64(y)
+    NE = len(x)
+    GL = y.size // max(NE, 1)
+    y2c = f64(y2) if y2 is not None else None
+    tk = f64(tokeep)
+    keep = np.zeros(max(NE, 1), np.int32)
+    c, m, a = C.c_double(0), C.c_double(0), C.c_double(0)
+    n = lib().ref_thin_grid(dp(x), dp(y), dp(y2c), NE, GL, dp(tk), len(tk), float(tol), ip(keep), C.byref(c), C.byref(m),
+                            C.byref(a))
+    return keep[:n].copy(), c.value, m.value, a.value

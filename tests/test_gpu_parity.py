@@ -383,3 +383,32 @@ def test_c4_sab_tabular_histogram(scatt, oracle, mode, kw):
     assert_parity(got[idx][:-1], ref[:-1], what=f"S(a,b) histogram {mode}")
     with pytest.raises(Exception):
         scatt.DeviceNuclide(small_heavy(), e_bins, ace.Params(order=16, scatt_type=ace.SCATT_TYPE_TABULAR))
+
+
+def test_apply_tol_and_thin_grid_match_oracle(scatt, oracle):
+    """N2: the steps after the integrator (apply_tol_scatt, thin_grid) on the device vs the oracle on
+    real moment matrices: identical zero pattern / kept points, values bit-identical (apply_tol) or
+    identical columns (thin_grid copies)."""
+    nuc = small_heavy(n_grid=900)
+    e_bins = synth.group_structure(70)
+    dn = scatt.DeviceNuclide(nuc, e_bins, ace.Params(order=5))
+    thr = min(nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT != ace.ELASTIC)
+    Eel, Einel = nuc.energy.copy(), nuc.energy[nuc.energy >= thr].copy()
+    el = dn.elastic(Eel)
+    inel, _ = dn.inelastic(Einel)
+    for mat in (el, inel):
+        ref = oracle.apply_tol_scatt(mat, 1e-8)
+        got = scatt.apply_tol_scatt(mat.copy(), 1e-8)
+        assert np.array_equal(got == 0.0, ref == 0.0)
+        assert np.array_equal(got, ref)
+    el_t = oracle.apply_tol_scatt(el, 1e-8)
+    inel_t = oracle.apply_tol_scatt(inel, 1e-8)
+    for x, y, y2 in ((Eel, el_t, None), (Einel, inel_t, inel_t * 1.5)):
+        keep, comp, _, mabs = oracle.thin_grid(x, y, e_bins, 1e-3, y2)
+        gx, gy, gy2, gcomp, gmabs = scatt.thin_grid(x, y, e_bins, 1e-3, y2)
+        assert len(gx) == len(keep) and np.array_equal(gx, x[keep])
+        assert np.array_equal(gy, y[keep]) and gcomp == comp
+        if y2 is not None:
+            assert np.array_equal(gy2, y2[keep])
+        assert abs(gmabs - mabs) <= 1e-12 * max(mabs, 1e-300) + 1e-18
+        assert 0 < len(keep) < len(x)

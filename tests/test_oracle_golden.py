@@ -323,3 +323,45 @@ def test_sab_tabular_properties(oracle, mode, kw):
     # mean cosine from the histogram (bin centres) agrees with P1 to within half a bin width
     centres = -1.0 + (np.arange(16) + 0.5) / 8.0
     assert np.all(np.abs((h * centres).sum(axis=(1, 2)) - leg[:, :, 1].sum(axis=1))[live] <= 1.0 / 16.0 + 1e-12)
+
+
+# ---- N2: apply_tol_scatt / thin_grid restatements (no reference tests exist: pinned by properties) -
+def test_apply_tol_scatt_properties(oracle):
+    rng = np.random.default_rng(3)
+    d = np.abs(rng.normal(size=(40, 9, 4)))
+    d[:, :, 0] /= d[:, :, 0].sum(axis=1)[:, None]
+    d[::3, 2, 0] = 3e-9
+    d[5] = 0.0
+    o = oracle.apply_tol_scatt(d, 1e-8)
+    assert np.all(o[::3, 2, :] == 0.0) and np.all(o[5] == 0.0)
+    live = d[:, :, 0].sum(axis=1) > 0
+    assert np.allclose(o[:, :, 0].sum(axis=1)[live], d[:, :, 0].sum(axis=1)[live], rtol=1e-15)
+    keep = ~((d[:, :, 0] > 0) & (d[:, :, 0] < 1e-8))
+    ratio = o[keep] / np.where(d[keep] == 0, 1, d[keep])
+    assert np.all(ratio[d[keep] != 0] >= 1.0 - 1e-15)          # survivors are only scaled up
+
+
+def test_thin_grid_properties(oracle):
+    x = np.geomspace(1e-5, 20.0, 600)
+    y = (np.sin(np.log(x))[:, None] ** 2 + 0.1) * np.linspace(1, 2, 12)[None, :]
+    y2 = y * (1.0 + 0.2 * np.cos(3 * np.log(x))[:, None])
+    tokeep = np.array([x[77], x[300], 5.0])
+    for yy2 in (None, y2):
+        keep, comp, maxerr, mabs = oracle.thin_grid(x, y, tokeep, 2e-3, yy2)
+        assert keep[0] == 0 and keep[-1] == len(x) - 1 and np.all(np.diff(keep) > 0)
+        assert 77 in keep and 300 in keep
+        assert comp == (len(x) - len(keep)) / len(x) and 0.0 < comp < 1.0
+        # every dropped point is reproduced by log-x interpolation between its kept neighbours' *test* pair:
+        # the reference tests point k against (last kept, k+1), so check that bound
+        kept = set(keep.tolist())
+        klo = 0
+        for k in range(1, len(x) - 1):
+            if k in kept:
+                klo = k
+                continue
+            f = np.log(x[k] / x[klo]) / np.log(x[k + 1] / x[klo])
+            for m in ([y] if yy2 is None else [y, yy2]):
+                t = m[klo] + (m[k + 1] - m[klo]) * f
+                assert np.all(np.abs(t - m[k]) / m[k] <= 2e-3 * (1 + 1e-12))
+        assert 0.0 < mabs and maxerr >= 0.0
+    assert len(oracle.thin_grid(x, y, tokeep, 2e-3, y2)[0]) >= len(oracle.thin_grid(x, y, tokeep, 2e-3)[0])
