@@ -171,6 +171,15 @@ int ndppgpu_thin_grid_dev(void *ctx, const double *d_x, const double *d_y1, cons
                           double *max_abs_err);
 int ndppgpu_gather_columns_dev(void *ctx, const double *d_src, const int *d_keep, int n_kept, int width, double *d_dst);
 
+/* calc_elastic_grid / calc_inelastic_grid followed by apply_tol_scatt and (if thin_tol > 0) thin_grid, i.e.
+ * src/ndpp.F90:607-648 for one matrix set, with only the kept columns copied back.  Ein is in/out: NE points
+ * in, the *n_kept points kept out; the matrices must have room for NE columns and hold n_kept on return. */
+int ndppgpu_elastic_thinned(void *nuc, double *Ein, int NE, double print_tol, double thin_tol, const double *tokeep,
+                            int n_tokeep, double *el_mat, int *n_kept, double *compression, double *max_abs_err);
+int ndppgpu_inelastic_thinned(void *nuc, double *Ein, int NE, double print_tol, double thin_tol, const double *tokeep,
+                              int n_tokeep, double *inel_mat, double *nuinel_mat /* nullable */, int *n_kept,
+                              double *compression, double *max_abs_err);
+
 /* Self-test of the shared-reciprocal division (csrc/legendre.cuh: FastDiv) against the IEEE operator on
  * per_thread random operand pairs per GPU thread.  counts2 = {pairs, mismatches}; mismatches must be zero. */
 int ndppgpu_test_exact_math(void *ctx, unsigned long long seed, int per_thread, unsigned long long *counts2);

@@ -25,7 +25,8 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_nuclide_get_table", "ndppgpu_nuclide_free", "ndppgpu_sab_create", "ndppgpu_sab", "ndppgpu_sab_dev",
            "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
-           "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev"]
+           "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
+           "ndppgpu_inelastic_thinned"]
 
 
 class NdppGpuError(RuntimeError):
@@ -94,6 +95,8 @@ def load() -> C.CDLL:
     L.ndppgpu_thin_grid.argtypes = [vp, c_dp, c_dp, c_dp, i, i, c_dp, i, d, c_ip, c_dp, c_dp]
     L.ndppgpu_thin_grid_dev.argtypes = [vp, vp, vp, vp, i, i, c_dp, i, d, vp, c_ip, c_dp, c_dp]
     L.ndppgpu_gather_columns_dev.argtypes = [vp, vp, vp, i, i, vp]
+    L.ndppgpu_elastic_thinned.argtypes = [vp, c_dp, i, d, d, c_dp, i, c_dp, c_ip, c_dp, c_dp]
+    L.ndppgpu_inelastic_thinned.argtypes = [vp, c_dp, i, d, d, c_dp, i, c_dp, c_dp, c_ip, c_dp, c_dp]
     _lib = L
     return L
 

@@ -1239,6 +1239,78 @@ int ndppgpu_thin_grid(void* ctx, double* x, double* y1, double* y2, int NE, int 
     return 0;
 }
 
+// calc_*_grid + apply_tol_scatt + thin_grid in one call (src/ndpp.F90:607-648 for one matrix set): the
+// moment arrays are integrated, cut at the printing tolerance and thinned on the device; only the kept
+// columns are copied to the host.
+static int scatt_thinned(Nuclide* n, bool inelastic, double* Ein, int NE, double print_tol, double thin_tol,
+                         const double* tokeep, int n_tokeep, double* mat, double* nu_mat, int* n_kept, double* compression,
+                         double* max_abs_err)
+{
+    Ctx* c = n->ctx;
+    CK(c, cudaSetDevice(c->device));
+    *n_kept = 0;
+    if (compression) *compression = 0.0;
+    if (max_abs_err) *max_abs_err = 0.0;
+    if (NE <= 0) return 0;
+    const int GL = n->G * n->L;
+    const size_t nout = (size_t)NE * GL;
+    TmpBuf d_E, d_out, d_nu, d_keep, o_E, o_out, o_nu;
+    if (tmp_upload(c, d_E, Ein, (size_t)NE) || tmp_alloc(c, d_out, nout * sizeof(double))) return 1;
+    if (nu_mat && tmp_alloc(c, d_nu, nout * sizeof(double))) return 1;
+    if (inelastic) {
+        if (inelastic_dev(n, d_E.as<double>(), NE, d_out.as<double>(), nu_mat ? d_nu.as<double>() : nullptr)) return 1;
+    } else {
+        if (elastic_dev(n, d_E.as<double>(), NE, d_out.as<double>())) return 1;
+    }
+    if (ndppgpu_apply_tol_dev(c, d_out.as<double>(), NE, n->G, n->L, print_tol)) return 1;
+    if (nu_mat && ndppgpu_apply_tol_dev(c, d_nu.as<double>(), NE, n->G, n->L, print_tol)) return 1;
+    const double* src = d_out.as<double>(); const double* src_nu = d_nu.as<double>();
+    *n_kept = NE;
+    if (thin_tol > 0.0) {   // src/ndpp.F90:622: "Thin the grid, unless thin_tol is zero"
+        if (tmp_alloc(c, d_keep, (size_t)NE * sizeof(int))) return 1;
+        if (ndppgpu_thin_grid_dev(c, d_E.as<double>(), d_out.as<double>(), nu_mat ? d_nu.as<double>() : nullptr, NE, GL,
+                                  tokeep, n_tokeep, thin_tol, d_keep.as<int>(), n_kept, compression, max_abs_err))
+            return 1;
+        const size_t m = (size_t)*n_kept * GL;
+        if (tmp_alloc(c, o_E, (size_t)*n_kept * sizeof(double)) || tmp_alloc(c, o_out, m * sizeof(double))) return 1;
+        if (ndppgpu_gather_columns_dev(c, d_E.as<double>(), d_keep.as<int>(), *n_kept, 1, o_E.as<double>()) ||
+            ndppgpu_gather_columns_dev(c, d_out.as<double>(), d_keep.as<int>(), *n_kept, GL, o_out.as<double>()))
+            return 1;
+        src = o_out.as<double>();
+        if (nu_mat) {
+            if (tmp_alloc(c, o_nu, m * sizeof(double))) return 1;
+            if (ndppgpu_gather_columns_dev(c, d_nu.as<double>(), d_keep.as<int>(), *n_kept, GL, o_nu.as<double>())) return 1;
+            src_nu = o_nu.as<double>();
+        }
+        CK(c, cudaMemcpyAsync(Ein, o_E.p, (size_t)*n_kept * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    const size_t m = (size_t)*n_kept * GL;
+    CK(c, cudaMemcpyAsync(mat, src, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (nu_mat) CK(c, cudaMemcpyAsync(nu_mat, src_nu, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (double)(m * sizeof(double) * (nu_mat ? 2 : 1));
+    return 0;
+}
+
+int ndppgpu_elastic_thinned(void* nuc, double* Ein, int NE, double print_tol, double thin_tol, const double* tokeep,
+                            int n_tokeep, double* el_mat, int* n_kept, double* compression, double* max_abs_err)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n || !Ein || !el_mat || !n_kept) return fail(n ? n->ctx : nullptr, "ndppgpu_elastic_thinned: null argument");
+    return scatt_thinned(n, false, Ein, NE, print_tol, thin_tol, tokeep, n_tokeep, el_mat, nullptr, n_kept, compression,
+                         max_abs_err);
+}
+
+int ndppgpu_inelastic_thinned(void* nuc, double* Ein, int NE, double print_tol, double thin_tol, const double* tokeep,
+                              int n_tokeep, double* inel_mat, double* nuinel_mat, int* n_kept, double* compression,
+                              double* max_abs_err)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n || !Ein || !inel_mat || !n_kept) return fail(n ? n->ctx : nullptr, "ndppgpu_inelastic_thinned: null argument");
+    return scatt_thinned(n, true, Ein, NE, print_tol, thin_tol, tokeep, n_tokeep, inel_mat, nuinel_mat, n_kept, compression,
+                         max_abs_err);
+}
+
 int ndppgpu_nuclide_free(void* nuc)
 {
     Nuclide* n = (Nuclide*)nuc;

@@ -412,3 +412,33 @@ def test_apply_tol_and_thin_grid_match_oracle(scatt, oracle):
             assert np.array_equal(gy2, y2[keep])
         assert abs(gmabs - mabs) <= 1e-12 * max(mabs, 1e-300) + 1e-18
         assert 0 < len(keep) < len(x)
+
+
+def test_driver_pipeline_matches_oracle_steps(scatt, oracle, tmp_path):
+    """src/ndpp.F90:560-702 for one nuclide: integrate, apply the printing tolerance, thin, write the
+    library -- through the fused device entry points -- against the same steps composed from the oracle."""
+    from ndpp_b200 import driver, output
+    nuc = small_heavy(n_grid=700)
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=5, nuscatter=True)
+    thr = min(nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT != ace.ELASTIC)
+    Eel, Einel = nuc.energy.copy(), nuc.energy[nuc.energy >= thr].copy()
+    path = str(tmp_path / "nuc.bin")
+    res = driver.preprocess_nuclide(nuc, e_bins, params, print_tol=1e-8, thin_tol=2e-3, Ein_el=Eel, Ein_inel=Einel,
+                                    library_file=path)
+    dn = scatt.DeviceNuclide(nuc, e_bins, params)       # the integration itself is covered elsewhere
+    el = oracle.apply_tol_scatt(dn.elastic(Eel), 1e-8)
+    inel, nu = dn.inelastic(Einel)
+    inel, nu = oracle.apply_tol_scatt(inel, 1e-8), oracle.apply_tol_scatt(nu, 1e-8)
+    ke = oracle.thin_grid(Eel, el, e_bins, 2e-3)[0]
+    ki = oracle.thin_grid(Einel, inel, e_bins, 2e-3, nu)[0]
+    assert np.array_equal(res.Ein_el, Eel[ke]) and np.array_equal(res.el_mat, el[ke])
+    assert np.array_equal(res.Ein_inel, Einel[ki]) and np.array_equal(res.inel_mat, inel[ki])
+    assert np.array_equal(res.nuinel_mat, nu[ki])
+    assert 0 < len(ke) < len(Eel) and res.thin_compr_el == (len(Eel) - len(ke)) / len(Eel)
+    lib = output.read_library(path)
+    assert lib["trailing_bytes"] == 0 and lib["nuscatter"] and np.array_equal(lib["Ein_inel"], Einel[ki])
+    assert np.array_equal(lib["grp_index_el"], output.group_index(Eel[ke], e_bins))
+    # the file stores the window between the first and last group of positive P0: what lies outside is zero
+    assert np.array_equal(lib["elastic"][:, :, 0] > 0, res.el_mat[:, :, 0] > 0)
+    assert np.allclose(lib["elastic"][lib["elastic"] != 0], res.el_mat[lib["elastic"] != 0], rtol=0, atol=0)
