@@ -9,9 +9,11 @@ continuum, P0-P7, 70 groups, 20 000 E_in points).  One evaluation = one output e
             library's stream, max over ranks.
   e2e       the same work through the reference-facing call calc_scatt(...) with HOST buffers:
             table upload + convert_distro + integration + D2H of the matrices, every step.
-  roofline  dominant kernel k_file6_cm (integrate_file6_cm_leg): algorithmic FP64 flops (SURVEY 8d
+  roofline  dominant kernel k_file6_cm_ws (integrate_file6_cm_leg): algorithmic FP64 flops (SURVEY 8d
             formula F_B) / its CUDA-event time, against the FP64 FMA rate measured in this
-            run by ndppgpu_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure).
+            run by ndppgpu_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure).  The path is
+            FP64-pipe bound, so `bound` is "fp64" (neither of the contract's hbm | tensor); the HBM view is
+            reported beside it.
   cpu_baseline / --impl reference
             the CPU oracle (restatement of the reference algorithm; the image has no Fortran compiler)
             on all host cores, on a bounded sample of the same E_in grids.
@@ -335,8 +337,16 @@ def run_b200(args):
     f6_ms = st["file6_cm_ms"] / max(1, st["file6_cm_launches"])
     peak = ctx.measure_fp64_peak(0.5)
     achieved = flops / (f6_ms * 1e-3) / 1e12 if f6_ms > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        if args.n_grid == 20000:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": None, "kernel": "k_file6_cm",
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+            "kernel": "k_file6_cm_ws (integrate_file6_cm_leg: records + tables + pipeline kernel)",
             "kernel_ms": f6_ms, "kernel_share_of_step": f6_ms / ms_step if ms_step else None,
             "algorithmic_flops_per_launch": flops, "active_E_in": n_act,
             "peak_source": "measured in this run: ndppgpu_measure_fp64_peak (DFMA chains, all SMs); "
