@@ -39,6 +39,7 @@ struct Ctx {
     ndppgpu_stats_t stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
     int sm_count = 148;
+    int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
     bool f6_solo = false;    // NDPPGPU_F6_SOLO=1: one role per warp on the same tables (A/B measurement)
     bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
 };
@@ -571,21 +572,38 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             k_fg_tasks<<<blocks_for(tasks, 256), 256, 0, c->stream>>>(n->dev, d_Ein, idx.as<int>(), n_idx,
                                                                        d_tasks.as<int>(), d_heads.as<int>());
             if (launch_check(c, "k_fg_tasks")) return 1;
-            // persistent warps with their level-parallel scratch (frontier 2^its frames x2, 2^(its+1) nodes)
+            // persistent warps with their level-parallel scratch.  The worst case of the inner recursion is a
+            // frontier of 2^its intervals (2^(its+1) nodes); real integrals stay far below, so the first attempt
+            // runs with 4096 / 32768 per warp (NDPPGPU_FG_CAP overrides, for the tests) and the kernel flags an overflow, in which case the call is
+            // repeated with the worst-case sizes.
             cudaDeviceProp prop;
             CK(c, cudaGetDeviceProperties(&prop, c->device));
-            const int blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * 3,
+            const int blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * FG_BLOCKS_PER_SM,
                                                         (tasks + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
-            const size_t warps = (size_t)blocks * FG_WARPS_PER_BLOCK, cap = (size_t)1 << n->p.adaptive_mu_its;
-            if (tmp_alloc(c, d_frames, warps * 2 * cap * sizeof(FgFrame)) ||
-                tmp_alloc(c, d_nvals, warps * 2 * cap * sizeof(double)) ||
-                tmp_alloc(c, d_nchilds, warps * 2 * cap * sizeof(int)))
-                return 1;
-            k_freegas_warp<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
-                n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, d_tasks.as<int>(), tasks,
-                d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
-                raw.as<double>());
-            if (launch_check(c, "k_freegas_warp")) return 1;
+            const size_t warps = (size_t)blocks * FG_WARPS_PER_BLOCK, full = (size_t)1 << n->p.adaptive_mu_its;
+            TmpBuf d_ovf;
+            if (tmp_alloc(c, d_ovf, sizeof(int))) return 1;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                const size_t capF = attempt ? full : std::min<size_t>(full, (size_t)c->fg_first_cap);
+                const size_t capN = attempt ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap);
+                if (tmp_alloc(c, d_frames, warps * 2 * capF * sizeof(FgFrame)) ||
+                    tmp_alloc(c, d_nvals, warps * capN * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)))
+                    return 1;
+                CK(c, cudaMemsetAsync(d_ovf.p, 0, sizeof(int), c->stream));
+                CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
+                k_freegas_warp<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
+                    n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, d_tasks.as<int>(), tasks,
+                    d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
+                    (int)capF, (int)capN, d_ovf.as<int>(), raw.as<double>());
+                if (launch_check(c, "k_freegas_warp")) return 1;
+                int ovf = 0;
+                CK(c, cudaMemcpyAsync(&ovf, d_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                CK(c, cudaStreamSynchronize(c->stream));
+                if (!ovf || (capF == full && capN == 2 * full)) {
+                    if (ovf) return fail(c, "ndppgpu: free-gas recursion outgrew its worst-case scratch");
+                    break;
+                }
+            }
             k_freegas_finish<<<blocks_for((long long)n_idx * 32, 128), 128, 0, c->stream>>>(
                 n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, raw.as<double>(), d_out);
             if (launch_check(c, "k_freegas_finish")) return 1;
@@ -778,6 +796,8 @@ int ndppgpu_init(int device, void** ctx)
     {
         const char* e = std::getenv("NDPPGPU_F6_LEGACY");
         c->f6_legacy = e && e[0] == '1';
+        e = std::getenv("NDPPGPU_FG_CAP");
+        if (e && std::atoi(e) >= 2) c->fg_first_cap = std::atoi(e);
         e = std::getenv("NDPPGPU_F6_SOLO");
         c->f6_solo = e && e[0] == '1';
     }

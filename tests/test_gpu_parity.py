@@ -442,3 +442,22 @@ def test_driver_pipeline_matches_oracle_steps(scatt, oracle, tmp_path):
     # the file stores the window between the first and last group of positive P0: what lies outside is zero
     assert np.array_equal(lib["elastic"][:, :, 0] > 0, res.el_mat[:, :, 0] > 0)
     assert np.allclose(lib["elastic"][lib["elastic"] != 0], res.el_mat[lib["elastic"] != 0], rtol=0, atol=0)
+
+
+def test_freegas_scratch_overflow_reruns_with_worst_case_sizes(scatt, monkeypatch):
+    """The level-parallel inner integral runs with a capped scratch first; an overflow must be detected
+    and the pass repeated with the worst-case sizes, giving the same bits."""
+    from ndpp_b200.capi import Context
+    nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=1000)
+    Ein = Ein[[300, 800]]
+    outs = []
+    for cap in ("4096", "8"):
+        monkeypatch.setenv("NDPPGPU_FG_CAP", cap)
+        ctx = Context(-1)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        outs.append(dn.elastic(Ein))
+        launches = ctx.stats()["launches"]
+        dn.clear()
+        outs.append(launches)
+    assert np.array_equal(outs[0], outs[2]) and np.any(outs[0] != 0)
+    assert outs[3] == outs[1] + 1        # one extra k_freegas_warp launch
