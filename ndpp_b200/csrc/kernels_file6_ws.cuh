@@ -155,7 +155,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #ifndef F6_NPROD
 #define F6_NPROD 1
 #endif
-#define F6_STAGES 4
+#ifndef F6_STAGE_BITS
+#define F6_STAGE_BITS 3   // ring of 2^bits windows per producer; A/B on C2 (one run each): 4 stages 183-189 ms, 8: 182.6, 16: 174.5, 32: 181.1 -- inside the run-to-run noise
+#endif
+#define F6_STAGES (1 << F6_STAGE_BITS)
 #define F6_CONS 4
 #define F6_THREADS ((F6_NPROD + 1) * 128)
 // Measured on B200 (C2, k_file6_cm 203 ms): 1 producer per consumer, 2 blocks/SM -> 183 ms; 2 producers with
@@ -384,7 +387,7 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
             }
         }
     } else {
-        // ring positions of the F6_NPROD producers, packed: 2 bits of stage + 1 bit of phase each
+        // ring positions of the F6_NPROD producers, packed: F6_STAGE_BITS of stage + 1 bit of phase each
         uint32_t pos = 0;
         const uint32_t full00 = smem_u32(&sh.full[cons][0][0]), empty00 = smem_u32(&sh.empty[cons][0][0]);
         const uint32_t buf00 = smem_u32(&sh.buf[cons][0][0][0]);
@@ -418,9 +421,11 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
 #pragma unroll
                 for (int l = 0; l < NDPP_MAX_L; ++l) fEl[l] = 0.0;
                 if (!I.skip) {
-                    for (int base = 0; base < M - 1; base += 31) {
+                    double pd = (double)lane;   // (double)(base + lane), advanced by the exact 31.0 per window
+                    for (int base = 0; base < M - 1; base += 31, pd += 31.0) {
                         const int p = base + lane;
-                        const uint32_t sp = (pos >> (3 * wq)) & 7u, st = sp & 3u, ph = sp >> 2;
+                        constexpr uint32_t PB = F6_STAGE_BITS + 1, PM = (1u << PB) - 1u;
+                        const uint32_t sp = (pos >> (PB * wq)) & PM, st = sp & (F6_STAGES - 1u), ph = sp >> F6_STAGE_BITS;
                         const uint32_t slot = (uint32_t)wq * F6_STAGES + st;
                         mbar_wait(full00 + 8u * slot, ph);
                         double fv, fnext;
@@ -428,12 +433,12 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
                         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fnext) : "r"(buf00 + 256u * slot + 8u * ((lane + 1) & 31)));
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty00 + 8u * slot);
-                        pos = (pos & ~(7u << (3 * wq))) | (((sp + 1u) & 7u) << (3 * wq));  // stage++, phase flips on wrap
+                        pos = (pos & ~(PM << (PB * wq))) | (((sp + 1u) & PM) << (PB * wq));  // stage++, phase flips on wrap
                         if (++wq == F6_NPROD) wq = 0;
                         // a segment whose two end values are zero adds exact zeros: skipped
                         if (lane < 31 && p + 1 < M && (fv != 0.0 || fnext != 0.0)) {
-                            const double x = I.mu_l_min + I.dmu * (double)p;
-                            const double xh = I.mu_l_min + I.dmu * (double)(p + 1);
+                            const double x = I.mu_l_min + I.dmu * pd;
+                            const double xh = I.mu_l_min + I.dmu * (pd + 1.0);
                             Powers A, B;
                             make_powers(x, A);
                             make_powers(xh, B);
