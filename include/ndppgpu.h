@@ -171,6 +171,32 @@ int ndppgpu_thin_grid_dev(void *ctx, const double *d_x, const double *d_y1, cons
                           double *max_abs_err);
 int ndppgpu_gather_columns_dev(void *ctx, const double *d_src, const int *d_keep, int n_kept, int width, double *d_dst);
 
+/* ---- fission-spectrum (chi) integration: replaces the E_in loop of calc_chi (src/chi.F90:120-153), i.e.
+ *      ChiData % integrate / prob / beta (src/chidata_header.F90:143-494) with nu_total / nu_delayed
+ *      (src/fission.F90:18-103), for one nuclide on the merged incoming-energy grid the caller built
+ *      (src/chi.F90:96-112).  A slot is one ChiData object: the prompt laws first, in the reference's order
+ *      (fission reaction by fission reaction, nested laws in chain order), then one delayed law per precursor
+ *      group.  energy / fission are nuc % energy and nuc % fission; nu_*_type are NU_NONE 0, NU_POLYNOMIAL 1,
+ *      NU_TABULAR 2 with nu_*_data as the reference stores them; precursor_data is nuc % nu_d_precursor_data.
+ *      Outputs in Fortran order: chi_total(G, NE), chi_prompt(G, NE), chi_delay(G, NE, n_precursor). ------- */
+typedef struct {
+    int law;        /* edist % law */
+    int delayed;    /* 0 = prompt, 1 = delayed */
+    int precursor;  /* 1-based precursor group (delayed) */
+    int threshold;  /* rxn % threshold, 1-based (prompt) */
+    int use_pvalid; /* associated(edist % next) .and. edist % p_valid % n_regions > 0 */
+    int n_sigma;    /* size of the cross section chi_prob reads (nuc % fission for MT 18, rxn % sigma otherwise) */
+    int sigma_off;  /* offsets, in doubles, into `pool`: that cross section, edist % data, p_valid as a TAB1 */
+    int data_off;
+    int pvalid_off;
+    int reserved;
+} ndppgpu_chi_slot;
+int ndppgpu_chi(void *ctx, int n_grid, const double *energy, const double *fission, int nu_t_type,
+                const double *nu_t_data, int n_nu_t, int nu_d_type, const double *nu_d_data, int n_nu_d,
+                int n_precursor, const double *precursor_data, int n_precursor_data, int n_slots,
+                const ndppgpu_chi_slot *slots, const double *pool, int n_pool, const double *e_bins, int n_bins,
+                const double *Ein, int NE, double *chi_total, double *chi_prompt, double *chi_delay);
+
 /* calc_elastic_grid / calc_inelastic_grid followed by apply_tol_scatt and (if thin_tol > 0) thin_grid, i.e.
  * src/ndpp.F90:607-648 for one matrix set, with only the kept columns copied back.  Ein is in/out: NE points
  * in, the *n_kept points kept out; the matrices must have room for NE columns and hold n_kept on return. */

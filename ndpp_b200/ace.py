@@ -22,6 +22,7 @@ SCATT_TYPE_LEGENDRE, SCATT_TYPE_TABULAR = 0, 1
 SAB_SECONDARY_EQUAL, SAB_SECONDARY_SKEWED, SAB_SECONDARY_CONT = 0, 1, 2
 SAB_ELASTIC_DISCRETE, SAB_ELASTIC_EXACT = 3, 4
 ELASTIC, N_LEVEL, N_FISSION, N_NC = 2, 4, 18, 91
+NU_NONE, NU_POLYNOMIAL, NU_TABULAR = 0, 1, 2   # src/constants.F90:187-189
 K_BOLTZMANN = 8.617343e-11  # MeV/K (the reference reads kT from the ACE table)
 
 
@@ -94,6 +95,29 @@ class Nuclide:
     reactions: List[Reaction]
     freegas_cutoff: float = 0.0   # MeV (src/ndpp.F90:573-591 turns the xml value into MeV)
     name: str = "synthetic"
+    # fission data read by calc_chi (src/ace_header.F90:113-130): nu_*_type are NU_NONE / NU_POLYNOMIAL / NU_TABULAR,
+    # nu_*_data as the reference stores them ([NC, c...] or a flattened TAB1); fission = nuc % fission (the sum
+    # of the fission cross sections on the nuclide grid; rebuilt from the reactions when None, src/ace.F90:823-828)
+    fission: Optional[np.ndarray] = None
+    nu_t_type: int = 0
+    nu_t_data: Optional[np.ndarray] = None
+    nu_d_type: int = 0
+    nu_d_data: Optional[np.ndarray] = None
+    nu_d_precursor_data: Optional[np.ndarray] = None   # per group: decay constant + TAB1 of its yield
+    nu_d_edist: List[DistEnergy] = field(default_factory=list)
+
+    @property
+    def n_precursor(self) -> int:
+        return len(self.nu_d_edist)
+
+    @property
+    def index_fission(self) -> List[int]:
+        """0-based positions of the fission reactions (is_fission: MT 18, 19, 20, 21, 38)."""
+        return [i for i, r in enumerate(self.reactions) if r.MT in (18, 19, 20, 21, 38)]
+
+    @property
+    def fissionable(self) -> bool:
+        return bool(self.index_fission)
 
 
 @dataclass

@@ -26,7 +26,7 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
            "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
-           "ndppgpu_inelastic_thinned"]
+           "ndppgpu_inelastic_thinned", "ndppgpu_chi"]
 
 
 class NdppGpuError(RuntimeError):
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     L.ndppgpu_sab_dev.argtypes = [vp, c_dp, i, i, i, vp, i, vp]
     L.ndppgpu_sab_free.argtypes = [vp]
     L.ndppgpu_measure_fp64_peak.argtypes = [vp, d, C.POINTER(d)]
+    L.ndppgpu_chi.argtypes = [vp, i, c_dp, c_dp, i, c_dp, i, i, c_dp, i, i, c_dp, i, i, vp, c_dp, i, c_dp, i, c_dp, i,
+                              c_dp, c_dp, c_dp]
     L.ndppgpu_interp_distro.argtypes = [vp, i, c_dp, i, c_dp]
     L.ndppgpu_nuclide_set_table.argtypes = [vp, i, i, c_dp]
     L.ndppgpu_test_legendre.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]

@@ -25,6 +25,7 @@
 #include "kernels_freegas.cuh"
 #include "kernels_post.cuh"
 #include "kernels_sab.cuh"
+#include "kernels_chi.cuh"
 
 using namespace ndpp;
 
@@ -1452,6 +1453,80 @@ int ndppgpu_sab_free(void* sab)
     cudaStreamSynchronize(s->ctx->stream);
     delete s;
     return 0;
+}
+
+// calc_chi (src/chi.F90:21-163) for one nuclide on a given (merged) E_in grid.
+int ndppgpu_chi(void* ctx, int n_grid, const double* energy, const double* fission, int nu_t_type, const double* nu_t_data,
+                int n_nu_t, int nu_d_type, const double* nu_d_data, int n_nu_d, int n_precursor,
+                const double* precursor_data, int n_precursor_data, int n_slots, const ndppgpu_chi_slot* slots,
+                const double* pool, int n_pool, const double* e_bins, int n_bins, const double* Ein, int NE,
+                double* chi_total, double* chi_prompt, double* chi_delay)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !energy || !fission || !slots || !e_bins || !Ein || !chi_total || !chi_prompt)
+        return fail(c, "ndppgpu_chi: null argument");
+    if (n_slots < 1 || n_slots > CHI_MAX_SLOTS) return fail(c, "ndppgpu_chi: number of energy laws out of range");
+    if (n_grid < 2 || n_bins < 2) return fail(c, "ndppgpu_chi: grid or group structure too short");
+    if (nu_t_type != 1 && nu_t_type != 2) return fail(c, "No neutron emission data for table");  // src/fission.F90:29
+    static_assert(sizeof(ndppgpu_chi_slot) == sizeof(ChiSlotDev), "slot layout");
+    int n_prompt = 0;
+    for (int i = 0; i < n_slots; ++i) {
+        if (!slots[i].delayed) {
+            if (i != n_prompt) return fail(c, "ndppgpu_chi: prompt laws must precede the delayed ones");
+            n_prompt++;
+        } else if (slots[i].precursor != i - n_prompt + 1) {
+            return fail(c, "ndppgpu_chi: delayed laws must be ordered by precursor group");
+        }
+    }
+    if (n_prompt < 1) return fail(c, "ndppgpu_chi: no prompt fission law");
+    if (n_slots - n_prompt != n_precursor) return fail(c, "Precursor Group Must Be Provided For Delayed Chi Data!");
+    if (n_precursor > 0 && !chi_delay) return fail(c, "ndppgpu_chi: chi_delay is null");
+    if (NE <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const int G = n_bins - 1;
+    // one staging buffer, one H2D copy: [energy | fission | nu_t | nu_d | precursor | pool | e_bins | Ein]
+    std::vector<double> h;
+    auto put = [&](const double* p, int n) { size_t o = h.size(); if (p && n > 0) h.insert(h.end(), p, p + n); return o; };
+    const size_t o_en = put(energy, n_grid), o_fi = put(fission, n_grid), o_nt = put(nu_t_data, n_nu_t),
+                 o_nd = put(nu_d_data, n_nu_d), o_pr = put(precursor_data, n_precursor_data), o_po = put(pool, n_pool),
+                 o_eb = put(e_bins, n_bins), o_ei = put(Ein, NE);
+    TmpBuf d_in, d_slots, d_out, d_err;
+    if (tmp_upload(c, d_in, h.data(), h.size())) return 1;
+    if (tmp_upload(c, d_slots, (const ChiSlotDev*)slots, (size_t)n_slots)) return 1;
+    const size_t n_tot = (size_t)NE * G, n_work = (size_t)NE * n_prompt * G, n_del = (size_t)n_precursor * NE * G;
+    if (tmp_alloc(c, d_out, (2 * n_tot + n_del + n_work) * sizeof(double))) return 1;
+    if (tmp_alloc(c, d_err, sizeof(int))) return 1;
+    CK(c, cudaMemsetAsync(d_err.p, 0, sizeof(int), c->stream));
+    ChiDev cd{};
+    const double* b = d_in.as<double>();
+    cd.n_grid = n_grid; cd.n_bins = n_bins; cd.n_slots = n_slots; cd.n_prompt = n_prompt; cd.n_precursor = n_precursor;
+    cd.nu_t_type = nu_t_type; cd.nu_d_type = nu_d_type; cd.NE = NE;
+    cd.energy = b + o_en; cd.fission = b + o_fi; cd.nu_t_data = b + o_nt; cd.nu_d_data = b + o_nd;
+    cd.precursor = b + o_pr; cd.pool = b + o_po; cd.e_bins = b + o_eb; cd.Ein = b + o_ei;
+    cd.slots = d_slots.as<ChiSlotDev>();
+    cd.chi_total = d_out.as<double>(); cd.chi_prompt = cd.chi_total + n_tot; cd.chi_delay = cd.chi_prompt + n_tot;
+    cd.work = cd.chi_delay + n_del;
+    cd.err = d_err.as<int>();
+    {
+        Timed tm(c, &c->pending_all);
+        k_chi<<<NE, 128, 0, c->stream>>>(cd);
+        if (launch_check(c, "k_chi")) return 1;
+    }
+    int herr = 0;
+    CK(c, cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(chi_total, cd.chi_total, n_tot * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(chi_prompt, cd.chi_prompt, n_tot * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (n_del) CK(c, cudaMemcpyAsync(chi_delay, cd.chi_delay, n_del * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (double)((2 * n_tot + n_del) * sizeof(double));
+    switch (herr) {
+    case 0: return 0;
+    case 1: return fail(c, "Value outside of array during binary search");
+    case 2: return fail(c, "Multiple interpolation regions not supported while attempting to sample continuous tabular "
+                           "distribution.");
+    case 3: return fail(c, "Discrete lines in continuous tabular distributed not yet supported");
+    default: return fail(c, "No neutron emission data for table");
+    }
 }
 
 int ndppgpu_measure_fp64_peak(void* ctx, double seconds, double* tflops)

@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import egrid, output
+from . import chi, egrid, output
 from .ace import SCATT_TYPE_LEGENDRE, Nuclide, Params
 from .capi import Context, check, dp, f64
 from .scatt import DeviceNuclide
@@ -30,6 +30,7 @@ class NuclideResult:
     thin_err_el: float = 0.0
     thin_compr_inel: float = 0.0
     thin_err_inel: float = 0.0
+    chi: Optional[tuple] = None   # (E_grid, chi_total, chi_prompt, chi_delay) when integrate_chi and fissionable
 
 
 def _thinned(dn: DeviceNuclide, inelastic: bool, Ein, print_tol, thin_tol, tokeep, nuscatter):
@@ -51,7 +52,8 @@ def _thinned(dn: DeviceNuclide, inelastic: bool, Ein, print_tol, thin_tol, tokee
 
 def preprocess_nuclide(nuc: Nuclide, energy_bins, params: Params, print_tol: float = PRINT_TOL_DEFAULT,
                        thin_tol: float = 0.0, Ein_el=None, Ein_inel=None, ctx: Optional[Context] = None,
-                       library_file: Optional[str] = None, lib_format: str = output.BINARY) -> NuclideResult:
+                       library_file: Optional[str] = None, lib_format: str = output.BINARY,
+                       integrate_chi: bool = False) -> NuclideResult:
     """One nuclide through src/ndpp.F90:560-702.  `thin_tol` is the fraction the reference derives from the
     user's percentage (`0.01 * thinning_tol`, :337); E_in grids default to create_Ein_grid (src/scatt.F90:166)."""
     if params.scatt_type != SCATT_TYPE_LEGENDRE:
@@ -68,8 +70,13 @@ def preprocess_nuclide(nuc: Nuclide, energy_bins, params: Params, print_tol: flo
     finally:
         dn.clear()
     res = NuclideResult(xe, el, xi, inel, nu, ce, ee, ci, ei)
+    do_chi = bool(integrate_chi) and nuc.fissionable               # src/ndpp.F90:705-712
+    if do_chi:
+        res.chi = chi.calc_chi(nuc, energy_bins, ctx)
     if library_file is not None:
         with output.LibraryWriter(library_file, nuc.name, nuc.kT, energy_bins, params.scatt_type, params.order,
-                                  params.nuscatter, params.mu_bins, thin_tol, lib_format) as w:
+                                  params.nuscatter, params.mu_bins, thin_tol, lib_format, chi_present=do_chi) as w:
             w.print_scatt(xe, el, xi, inel, nu)
+            if do_chi:
+                w.print_chi(*res.chi)
     return res

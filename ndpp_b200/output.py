@@ -11,8 +11,13 @@ Host-side mirror of the reference's writers, fed straight from the (thinned) mom
   read_library          restatement of the reference's reader src/utils/ndpp_data.py:141-245 (binary)
 
 tests/test_output.py reads files written here with the reference's own reader (imported from
-/root/reference in the build container) and compares every number; chi is not written (the reference
-integrates it elsewhere, src/chidata_header.F90 -- outside this path), so chi_present is always 0.
+/root/reference in the build container) and compares every number.
+
+  print_chi          <- src/chi.F90:165-337 (ASCII :195-236, BINARY :309-337): NE, number of precursor groups,
+                        E_grid, chi_total(G, NE), chi_prompt(G, NE), chi_delay(G, NE, precursor), written after
+                        the scattering data of a fissionable nuclide when integrate_chi is set (chi_present = 1,
+                        src/ndpp.F90:1275-1279).  The reference's Python reader takes only NE values per chi
+                        array (src/utils/ndpp_data.py:247-270), so chi records are checked with read_library here.
 """
 from __future__ import annotations
 
@@ -72,7 +77,8 @@ class LibraryWriter:
     """init_library + print_scatt for one nuclide (or S(a,b) table) file."""
 
     def __init__(self, filename, name: str, kT: float, energy_bins, scatt_type: int, scatt_order: int,
-                 nuscatter: bool, mu_bins: int, thin_tol: float, lib_format: str = BINARY, sab: bool = False):
+                 nuscatter: bool, mu_bins: int, thin_tol: float, lib_format: str = BINARY, sab: bool = False,
+                 chi_present: bool = False):
         self.fmt = lib_format.lower()
         if self.fmt not in (ASCII, BINARY):
             raise ValueError("lib_format must be 'ascii' or 'binary' (HDF5 output is not built)")
@@ -80,7 +86,8 @@ class LibraryWriter:
         self.NG = len(self.eb) - 1
         self.nuscatter = bool(nuscatter) and not sab      # ndpp.F90:1272-1276
         name10 = (name + " " * 10)[:10]
-        hdr_ints = (int(scatt_type), int(scatt_order), int(self.nuscatter), 0)
+        self.chi_present = bool(chi_present) and not sab  # integrate_chi .and. fissionable, ndpp.F90:1275-1279
+        hdr_ints = (int(scatt_type), int(scatt_order), int(self.nuscatter), int(self.chi_present))
         if self.fmt == BINARY:
             self.f = open(filename, "wb")
             self.f.write(name10.encode("ascii"))
@@ -140,6 +147,25 @@ class LibraryWriter:
             else:
                 self.f.write(f"{0:20d}\n")
 
+    def print_chi(self, E_grid, chi_t, chi_p, chi_d):
+        """chi_t / chi_p are [NE][G] (the Fortran chi(G, NE)), chi_d is [precursor][NE][G]."""
+        if not self.chi_present:
+            raise ValueError("print_chi on a library whose header says chi_present = 0")
+        E_grid = np.asarray(E_grid, dtype=np.float64)
+        chi_t, chi_p, chi_d = (np.ascontiguousarray(a, dtype=np.float64) for a in (chi_t, chi_p, chi_d))
+        n_prec = chi_d.shape[0] if chi_d.size else 0
+        if self.fmt == BINARY:
+            self.f.write(struct.pack("=2i", len(E_grid), n_prec))
+            for a in (E_grid, chi_t, chi_p, chi_d):
+                self.f.write(a.astype("=f8").tobytes())
+        else:
+            self.f.write(f"{len(E_grid):20d}{n_prec:20d}\n")
+            _ascii_array(self.f, E_grid, _fortran_e)
+            _ascii_array(self.f, chi_t.ravel(), _fortran_e)
+            _ascii_array(self.f, chi_p.ravel(), _fortran_e)
+            for k in range(n_prec):
+                _ascii_array(self.f, chi_d[k].ravel(), _fortran_e)
+
     def close(self):
         self.f.close()
 
@@ -189,5 +215,11 @@ def read_library(filename) -> dict:
             out["inelastic"] = matrix(len(out["Ein_inel"]))
             if out["nuscatter"]:
                 out["nuinelastic"] = matrix(len(out["Ein_inel"]))
+        if out["chi_present"]:
+            NE, n_prec = rd("2i")
+            out["Ein_chi"] = np.array(rd(f"{NE}d"))
+            out["chi_total"] = np.array(rd(f"{NE * NG}d")).reshape(NE, NG)
+            out["chi_prompt"] = np.array(rd(f"{NE * NG}d")).reshape(NE, NG)
+            out["chi_delay"] = np.array(rd(f"{n_prec * NE * NG}d")).reshape(n_prec, NE, NG)
         out["trailing_bytes"] = len(f.read())
     return out

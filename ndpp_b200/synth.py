@@ -339,3 +339,91 @@ def c5_shape(spec, e_max=20.0):
         n_inel = max(1, int(ne * frac))
     return NuclideShape(index=i, n_el=ne, n_inel=n_inel, level_thresholds=lev, cont_threshold=cont, e_lo=1.0e-11,
                         e_hi=e_max)
+
+
+# --------------------------------------------------------------------------------------------------
+# fissionable nuclides for chi (row N4): synthetic shapes, no evaluated data
+# --------------------------------------------------------------------------------------------------
+def _watt_rows(e_in, n_out, a0=0.988, b=2.249, e_max=20.0):
+    """Law-4 rows with a Watt-shaped spectrum whose temperature drifts with E_in (lin-lin, cdf by trapezoid)."""
+    rows = []
+    for k, E in enumerate(e_in):
+        a = a0 * (1.0 + 0.01 * k)
+        Eout = np.concatenate([[0.0], np.geomspace(1.0e-5, e_max, n_out - 1)])
+        pdf = np.exp(-Eout / a) * np.sinh(np.sqrt(b * Eout))
+        cdf = _lin_cdf(Eout, pdf)
+        pdf, cdf = pdf / cdf[-1], cdf / cdf[-1]
+        cdf[-1] = 1.0
+        rows.append((2, Eout, pdf, cdf, np.zeros(0), np.zeros(0)))
+    return rows
+
+
+def _tab1_data(x, y, interp=None):
+    """[NR, (NBT, INT), NE, x, y] as the reference keeps nu / yield / temperature tables in a flat array."""
+    head = [0.0] if interp is None else [1.0, float(len(x)), float(interp)]
+    return np.concatenate([head, [float(len(x))], np.asarray(x, float), np.asarray(y, float)])
+
+
+def fissile_total(n_grid=300, n_ein=12, n_out=80, n_precursor=6, seed=SEED0 + 6):
+    """U-235 shape: one total-fission reaction (MT 18) with a law-4 spectrum, tabular nu-bar, tabular delayed
+    nu-bar, `n_precursor` delayed groups each with its own law-4 spectrum and energy-dependent yield."""
+    rng = np.random.default_rng(seed)
+    energy = np.geomspace(1.0e-11, 20.0, n_grid)
+    energy[0], energy[-1] = 1.0e-11, 20.0
+    fis = 1.2 + 580.0 * np.sqrt(2.53e-8 / energy)
+    e_in = np.concatenate([[1.0e-11], np.geomspace(1.0e-6, 20.0, n_ein - 1)])
+    e_in[-1] = 20.0
+    ed = DistEnergy(law=4, data=make_law44(e_in, _watt_rows(e_in, n_out)),
+                    p_valid=Tab1(x=np.array([1.0e-11, 20.0]), y=np.array([1.0, 1.0])))
+    rxn = Reaction(MT=18, Q_value=193.0, multiplicity=19, threshold=1, scatter_in_cm=False, sigma=fis.copy(), edist=ed)
+    nu_e = np.array([1.0e-11, 1.0, 5.0, 20.0])
+    prec, dl = [], []
+    for k in range(n_precursor):
+        ye = np.array([1.0e-11, 4.0, 20.0])
+        yk = rng.uniform(0.05, 0.3, 3)
+        prec.append(np.concatenate([[0.0125 * 3.0 ** k], _tab1_data(ye, yk)]))
+        e_d = np.array([1.0e-11, 20.0]) if k % 2 == 0 else np.array([1.0e-11, 2.0e-6 * (k + 1), 20.0])
+        dl.append(DistEnergy(law=4, data=make_law44(e_d, _watt_rows(e_d, 40, a0=0.4 + 0.05 * k, b=1.0, e_max=8.0)),
+                             p_valid=Tab1(x=np.array([1.0e-11, 20.0]), y=np.array([1.0, 1.0]))))
+    return Nuclide(awr=233.0248, kT=KT_293K, energy=energy, elastic=np.full(n_grid, 11.0),
+                   reactions=[Reaction(MT=ELASTIC, threshold=1), rxn], name="U-235-shape",
+                   nu_t_type=2, nu_t_data=_tab1_data(nu_e, [2.43, 2.55, 3.10, 5.2]),
+                   nu_d_type=2, nu_d_data=_tab1_data(nu_e, [0.0167, 0.0167, 0.0150, 0.0090]),
+                   nu_d_precursor_data=np.concatenate(prec), nu_d_edist=dl)
+
+
+def fissile_partial(n_grid=240, seed=SEED0 + 7):
+    """Pu-240 shape: partial fission reactions MT 19 / 20 / 21 / 38 with the analytic laws -- Maxwell (7),
+    evaporation (9), Watt (11) -- and a nested chain (law 4 valid with probability p(E), then law 7) whose
+    p_valid carries an interpolation region, as the reference's `Pu-240 issue` comments describe
+    (src/chi.F90:47-49, src/chidata_header.F90:199,210); polynomial nu-bar, no delayed data.  The restriction
+    energies are chosen so that the reference's formulas stay finite: its law 7 and law 11 replace a group edge
+    by U itself (src/chidata_header.F90:358,362,431,438), which is NaN for the negative U of evaluated fission
+    data whenever the replacement triggers."""
+    rng = np.random.default_rng(seed)
+    energy = np.geomspace(1.0e-11, 20.0, n_grid)
+    energy[0], energy[-1] = 1.0e-11, 20.0
+    e_t = np.array([1.0e-11, 1.0, 20.0])
+    maxwell = lambda U: np.concatenate([_tab1_data(e_t, [1.29, 1.33, 1.62]), [U]])
+    evap = lambda U: np.concatenate([_tab1_data(e_t, [0.9, 1.0, 1.4], interp=2), [U]])
+    watt = lambda U: np.concatenate([_tab1_data(e_t, [0.96, 0.98, 1.05]), _tab1_data(e_t, [2.2, 2.25, 2.5]), [U]])
+    one = Tab1(x=np.array([1.0e-11, 20.0]), y=np.array([1.0, 1.0]))
+    thr20, thr21, thr38 = (int(np.searchsorted(energy, e)) + 1 for e in (5.5, 11.5, 17.0))
+    e4 = np.array([1.0e-11, 0.5, 6.0, 20.0])
+    chain = DistEnergy(law=4, data=make_law44(e4, _watt_rows(e4, 60)),
+                       p_valid=Tab1(x=np.array([1.0e-11, 3.0, 20.0]), y=np.array([1.0, 0.7, 0.4]),
+                                    nbt=np.array([3], np.int32), int=np.array([2], np.int32)),
+                       next=DistEnergy(law=7, data=maxwell(-20.0),
+                                       p_valid=Tab1(x=np.array([1.0e-11, 3.0, 20.0]), y=np.array([0.0, 0.3, 0.6]),
+                                                    nbt=np.array([3], np.int32), int=np.array([2], np.int32))))
+    sig = lambda thr, s: s * (1.0 + 0.1 * rng.random(n_grid - thr + 1))
+    rx = [Reaction(MT=ELASTIC, threshold=1),
+          Reaction(MT=19, Q_value=190.0, multiplicity=19, threshold=1, scatter_in_cm=False, sigma=sig(1, 1.5), edist=chain),
+          Reaction(MT=20, Q_value=185.0, multiplicity=19, threshold=thr20, scatter_in_cm=False, sigma=sig(thr20, 0.6),
+                   edist=DistEnergy(law=9, data=evap(5.4), p_valid=one)),
+          Reaction(MT=21, Q_value=180.0, multiplicity=19, threshold=thr21, scatter_in_cm=False, sigma=sig(thr21, 0.4),
+                   edist=DistEnergy(law=11, data=watt(2.0), p_valid=one)),
+          Reaction(MT=38, Q_value=175.0, multiplicity=19, threshold=thr38, scatter_in_cm=False, sigma=sig(thr38, 0.2),
+                   edist=DistEnergy(law=7, data=maxwell(16.0), p_valid=one))]
+    return Nuclide(awr=237.9916, kT=KT_293K, energy=energy, elastic=np.full(n_grid, 10.0), reactions=rx, name="Pu-240-shape",
+                   nu_t_type=1, nu_t_data=np.array([3.0, 2.8, 0.14, 0.002]))

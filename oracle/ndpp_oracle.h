@@ -144,6 +144,24 @@ void ref_apply_tol_scatt(double *data, int L, int G, int NE, double tol);
 int ref_thin_grid(const double *x, const double *y1, const double *y2, int NE, int GL, const double *tokeep, int n_tokeep,
                   double tol, int *keep, double *compression, double *maxerr, double *max_abs);
 
+/* ---- chi (fission spectrum) integration: calc_chi (src/chi.F90:21-163), src/chidata_header.F90:143-494 ---- */
+typedef struct {
+    int law;        /* edist % law */
+    int delayed;    /* 0 = prompt law of a fission reaction, 1 = delayed-neutron law of a precursor group */
+    int precursor;  /* 1-based precursor group (delayed) */
+    int threshold;  /* rxn % threshold, 1-based (prompt) */
+    int use_pvalid; /* associated(edist % next) .and. p_valid % n_regions > 0 */
+    int n_sigma;    /* length of the cross section the probability is taken from */
+    int sigma_off;  /* offsets (in doubles) into the pool: sigma, edist % data, flattened p_valid TAB1 */
+    int data_off;
+    int pvalid_off;
+    int reserved;
+} ref_chi_slot;
+int ref_calc_chi(int n_grid, const double *energy, const double *fission, int nu_t_type, const double *nu_t_data,
+                 int nu_d_type, const double *nu_d_data, int n_precursor, const double *precursor_data, int n_slots,
+                 const ref_chi_slot *slots, const double *pool, const double *E_bins, int n_bins, const double *Ein_grid,
+                 int NE, double *chi_total, double *chi_prompt, double *chi_delay);
+
 #ifdef __cplusplus
 }
 #endif

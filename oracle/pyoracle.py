@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         L.ref_apply_tol_scatt.argtypes = [c_dp, C.c_int, C.c_int, C.c_int, C.c_double]
         L.ref_apply_tol_scatt.restype = None
         L.ref_thin_grid.argtypes = [c_dp, c_dp, c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_double, c_ip, c_dp, c_dp, c_dp]
+        L.ref_calc_chi.argtypes = [C.c_int, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, C.c_void_p,
+                                   c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp, c_dp]
         L.ref_freegas_counters.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
         L.ref_freegas_counters.restype = None
         _lib = L
@@ -357,3 +359,25 @@ def thin_grid(x, y, tokeep, tol, y2=None):
     n = lib().ref_thin_grid(dp(x), dp(y), dp(y2c), NE, GL, dp(tk), len(tk), float(tol), ip(keep), C.byref(c), C.byref(m),
                             C.byref(a))
     return keep[:n].copy(), c.value, m.value, a.value
+
+
+def calc_chi(nuc, E_bins, E_grid=None):
+    """calc_chi (src/chi.F90:21-163) through the C restatement; the slot list, pool and merged grid are the
+    host mirror's (ndpp_b200.chi: data marshalling only, no arithmetic on the moments)."""
+    from ndpp_b200 import chi as hostchi
+    slots, pool = hostchi.chi_data(nuc)
+    E_grid = hostchi.chi_grid(slots) if E_grid is None else f64(E_grid)
+    E_bins = f64(E_bins)
+    G, NE, n_prec = len(E_bins) - 1, len(E_grid), nuc.n_precursor
+    energy, fis = f64(nuc.energy), hostchi.fission_xs(nuc)
+    nu_t = f64(nuc.nu_t_data)
+    nu_d = f64(nuc.nu_d_data) if nuc.nu_d_data is not None else np.zeros(1)
+    prec = f64(nuc.nu_d_precursor_data) if nuc.nu_d_precursor_data is not None else np.zeros(1)
+    chi_t, chi_p, chi_d = np.empty((NE, G)), np.empty((NE, G)), np.empty((max(n_prec, 1), NE, G))
+    sc = hostchi.slots_c(slots)
+    rc = lib().ref_calc_chi(len(energy), dp(energy), dp(fis), int(nuc.nu_t_type), dp(nu_t), int(nuc.nu_d_type), dp(nu_d),
+                            n_prec, dp(prec), len(slots), C.cast(sc, C.c_void_p), dp(pool), dp(E_bins), len(E_bins),
+                            dp(E_grid), NE, dp(chi_t), dp(chi_p), dp(chi_d))
+    if rc:
+        check_errors()
+    return E_grid, chi_t, chi_p, chi_d[:n_prec]

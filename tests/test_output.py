@@ -123,3 +123,33 @@ def test_reference_reader_reads_our_files(tmp_path, nus):
             else:
                 assert (rec.gmin, rec.gmax) == (g[0], g[-1])
                 assert np.array_equal(rec.outgoing, m[iE, g[0]:g[-1] + 1])
+
+
+def test_chi_record_round_trip(tmp_path):
+    """print_chi (src/chi.F90:195-236 ASCII, :309-337 binary) behind the scattering data, chi_present = 1."""
+    rng = np.random.default_rng(3)
+    eb = np.array([0.0, 1e-6, 1.0, 20.0])
+    NE, G, L, NEc, NP = 4, 3, 2, 5, 2
+    Ein = np.geomspace(1e-9, 19.0, NE)
+    el = rng.random((NE, G, L))
+    Ec = np.geomspace(1e-11, 20.0, NEc)
+    ct, cp, cd = rng.random((NEc, G)), rng.random((NEc, G)), rng.random((NP, NEc, G))
+    pb, pa = str(tmp_path / "n.bin"), str(tmp_path / "n.txt")
+    for path, fmt in ((pb, output.BINARY), (pa, output.ASCII)):
+        with output.LibraryWriter(path, "92235.70c", 2.53e-8, eb, 0, L - 1, False, 201, 0.0, fmt, chi_present=True) as w:
+            w.print_scatt(Ein, el)
+            w.print_chi(Ec, ct, cp, cd)
+    lib = output.read_library(pb)
+    assert lib["chi_present"] and lib["trailing_bytes"] == 0
+    assert np.array_equal(lib["Ein_chi"], Ec) and np.array_equal(lib["chi_total"], ct)
+    assert np.array_equal(lib["chi_prompt"], cp) and np.array_equal(lib["chi_delay"], cd)
+    lines = open(pa).read().split("\n")
+    k = [i for i, ln in enumerate(lines) if ln == f"{NEc:20d}{NP:20d}"]
+    assert len(k) == 1
+    vals = np.array([float(ln[20 * j:20 * j + 20]) for ln in lines[k[0] + 1:] for j in range(len(ln) // 20)])
+    want = np.concatenate([Ec, ct.ravel(), cp.ravel(), cd.ravel()])
+    # every array starts on a new line (print_ascii_array), values carry 13 digits
+    assert len(vals) == len(want) and np.allclose(vals, want, rtol=1e-12)
+    with pytest.raises(ValueError):
+        with output.LibraryWriter(pb, "x", 0.0, eb, 0, 1, False, 201, 0.0) as w:
+            w.print_chi(Ec, ct, cp, cd)
