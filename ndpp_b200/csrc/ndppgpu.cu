@@ -155,9 +155,12 @@ struct Slot {
     std::vector<int> row_off;  // NE+1
     int max_np = 0, max_u = 0;
     int iso_rows = 0;          // every row of the angular table is the isotropic 0.5 (free-gas shortcut)
-    // device
-    DevBuf d_e_grid, d_row_off, d_intt, d_tab, d_eout, d_pdf, d_cdf, d_sigma, d_pvalid, d_yield, d_ad_energy,
-        d_ad_type, d_ad_loc, d_ad_data, d_ed_data;
+    // device: offsets into the nuclide's two arenas (inputs: one H2D copy; tables: one zero-fill), see
+    // ndppgpu_convert_distro
+    static constexpr size_t NONE = ~(size_t)0;
+    size_t o_e_grid = NONE, o_row_off = NONE, o_intt = NONE, o_sigma = NONE, o_pvalid = NONE, o_yield = NONE,
+           o_ad_energy = NONE, o_ad_type = NONE, o_ad_loc = NONE, o_ad_data = NONE, o_ed_data = NONE;
+    size_t t_tab = 0, t_eout = 0, t_pdf = 0, t_cdf = 0;
     SlotDev dev{};
     bool converted = false;
 };
@@ -167,7 +170,9 @@ struct Nuclide {
     ndppgpu_params p;
     double awr, kT, freegas_cutoff;
     std::vector<double> energy, elastic, e_bins, mu;
-    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_rmu, d_slots, d_el_ids, d_in_ids, d_err;
+    DevBuf d_energy, d_elastic, d_e_bins, d_mu, d_rmu, d_slots, d_err;
+    DevBuf d_arena, d_tables;   // every small per-slot array / every uniform-mu table of the nuclide
+    const int *d_el_ids = nullptr, *d_in_ids = nullptr;
     NucDev dev{};
     std::vector<std::unique_ptr<HostRxn>> rxns;
     std::vector<std::unique_ptr<Slot>> slots;
@@ -246,49 +251,78 @@ void scatt_init(Nuclide* n, Slot* s, HostRxn* rxn, int edist_assoc, int edist_la
     s->is_init = 1;
 }
 
-int build_slot_device(Nuclide* n, Slot* s)
+// Host staging arena of one nuclide: every small array of every slot is appended (16-byte aligned) and the
+// whole arena crosses PCIe in one copy -- per-array uploads with their stream synchronisations cost ~10 ms per
+// heavy nuclide (42 slots x 10 arrays), which dominated a library run's set-up.
+struct Arena {
+    std::vector<unsigned char> h;
+    template <class T> size_t put(const T* p, size_t n)
+    {
+        const size_t off = (h.size() + 15) & ~(size_t)15;
+        h.resize(off + n * sizeof(T));
+        if (n) memcpy(h.data() + off, p, n * sizeof(T));
+        return off;
+    }
+};
+
+inline size_t reserve_bytes(size_t& total, size_t bytes)
 {
-    Ctx* c = n->ctx;
+    const size_t off = (total + 255) & ~(size_t)255;
+    total = off + bytes;
+    return off;
+}
+
+// pass 1: place the slot's inputs in the arena and its tables in the table block
+void layout_slot(Nuclide* n, Slot* s, Arena& A, size_t& table_bytes)
+{
     HostRxn* r = s->rxn;
     const int M = n->p.mu_bins;
     const size_t total_np = (size_t)s->row_off.back();
-    if (upload(c, s->d_e_grid, s->e_grid.data(), s->e_grid.size())) return 1;
-    if (upload(c, s->d_row_off, s->row_off.data(), s->row_off.size())) return 1;
+    s->o_e_grid = A.put(s->e_grid.data(), s->e_grid.size());
+    s->o_row_off = A.put(s->row_off.data(), s->row_off.size());
     std::vector<int> intt(s->NE, HISTOGRAM);  // convert_file4 tail (:754-760)
-    if (upload(c, s->d_intt, intt.data(), intt.size())) return 1;
-    if (dev_alloc(c, s->d_tab, total_np * M * sizeof(double))) return 1;
-    if (dev_alloc(c, s->d_eout, total_np * sizeof(double))) return 1;
-    if (dev_alloc(c, s->d_pdf, total_np * sizeof(double))) return 1;
-    if (dev_alloc(c, s->d_cdf, total_np * sizeof(double))) return 1;
-    CK(c, cudaMemsetAsync(s->d_tab.p, 0, s->d_tab.bytes, c->stream));
-    CK(c, cudaMemsetAsync(s->d_eout.p, 0, s->d_eout.bytes, c->stream));
-    CK(c, cudaMemsetAsync(s->d_pdf.p, 0, s->d_pdf.bytes, c->stream));
-    CK(c, cudaMemsetAsync(s->d_cdf.p, 0, s->d_cdf.bytes, c->stream));
-    if (r->MT != 2) { if (upload(c, s->d_sigma, r->sigma.data(), r->sigma.size())) return 1; }
-    if (!s->p_valid.empty()) if (upload(c, s->d_pvalid, s->p_valid.data(), s->p_valid.size())) return 1;
-    if (!r->yield.empty()) if (upload(c, s->d_yield, r->yield.data(), r->yield.size())) return 1;
+    s->o_intt = A.put(intt.data(), intt.size());
+    s->t_tab = reserve_bytes(table_bytes, total_np * M * sizeof(double));
+    s->t_eout = reserve_bytes(table_bytes, total_np * sizeof(double));
+    s->t_pdf = reserve_bytes(table_bytes, total_np * sizeof(double));
+    s->t_cdf = reserve_bytes(table_bytes, total_np * sizeof(double));
+    if (r->MT != 2) s->o_sigma = A.put(r->sigma.data(), r->sigma.size());
+    if (!s->p_valid.empty()) s->o_pvalid = A.put(s->p_valid.data(), s->p_valid.size());
+    if (!r->yield.empty()) s->o_yield = A.put(r->yield.data(), r->yield.size());
     if (s->has_adist) {
-        if (upload(c, s->d_ad_energy, r->ad_energy.data(), r->ad_energy.size())) return 1;
-        if (upload(c, s->d_ad_type, r->ad_type.data(), r->ad_type.size())) return 1;
-        if (upload(c, s->d_ad_loc, r->ad_loc.data(), r->ad_loc.size())) return 1;
-        if (upload(c, s->d_ad_data, r->ad_data.data(), r->ad_data.size())) return 1;
+        s->o_ad_energy = A.put(r->ad_energy.data(), r->ad_energy.size());
+        s->o_ad_type = A.put(r->ad_type.data(), r->ad_type.size());
+        s->o_ad_loc = A.put(r->ad_loc.data(), r->ad_loc.size());
+        s->o_ad_data = A.put(r->ad_data.data(), r->ad_data.size());
     }
-    if (!s->edist_data.empty()) if (upload(c, s->d_ed_data, s->edist_data.data(), s->edist_data.size())) return 1;
+    if (!s->edist_data.empty()) s->o_ed_data = A.put(s->edist_data.data(), s->edist_data.size());
+}
+
+// pass 2: device pointers of the slot
+int build_slot_device(Nuclide* n, Slot* s)
+{
+    HostRxn* r = s->rxn;
+    const int M = n->p.mu_bins;
+    const size_t total_np = (size_t)s->row_off.back();
+    unsigned char* const A = n->d_arena.as<unsigned char>();
+    unsigned char* const T = n->d_tables.as<unsigned char>();
+    auto in = [&](size_t off) -> void* { return off == Slot::NONE ? nullptr : (void*)(A + off); };
 
     SlotDev& d = s->dev;
     d.NE = s->NE; d.M = M; d.law = s->law; d.has_adist = s->has_adist; d.has_edist = s->has_edist;
     d.scatter_in_cm = r->scatter_in_cm; d.MT = r->MT; d.threshold = r->threshold;
     d.n_sigma = (r->MT == 2) ? (int)n->energy.size() : (int)r->sigma.size();
     d.multiplicity = r->multiplicity; d.total_np = (int)total_np; d.max_np = s->max_np; d.Q = r->Q;
-    d.e_grid = s->d_e_grid.as<double>(); d.row_off = s->d_row_off.as<int>(); d.intt = s->d_intt.as<int>();
-    d.tab = s->d_tab.as<double>(); d.eout = s->d_eout.as<double>(); d.pdf = s->d_pdf.as<double>();
-    d.cdf = s->d_cdf.as<double>();
-    d.sigma = (r->MT == 2) ? n->d_elastic.as<double>() : s->d_sigma.as<double>();
-    d.p_valid = s->p_valid.empty() ? nullptr : s->d_pvalid.as<double>();
-    d.yield = r->yield.empty() ? nullptr : s->d_yield.as<double>();
-    d.ad_energy = s->d_ad_energy.as<double>(); d.ad_type = s->d_ad_type.as<int>(); d.ad_loc = s->d_ad_loc.as<int>();
-    d.ad_data = s->d_ad_data.as<double>(); d.ad_n = (int)r->ad_energy.size();
-    d.ed_data = s->d_ed_data.as<double>(); d.edist_law = s->edist_law;
+    d.e_grid = (const double*)in(s->o_e_grid); d.row_off = (const int*)in(s->o_row_off); d.intt = (const int*)in(s->o_intt);
+    d.tab = (double*)(T + s->t_tab); d.eout = (const double*)(T + s->t_eout); d.pdf = (const double*)(T + s->t_pdf);
+    d.cdf = (const double*)(T + s->t_cdf);
+    d.sigma = (r->MT == 2) ? n->d_elastic.as<double>() : (const double*)in(s->o_sigma);
+    d.p_valid = (const double*)in(s->o_pvalid);
+    d.yield = (const double*)in(s->o_yield);
+    d.ad_energy = (const double*)in(s->o_ad_energy); d.ad_type = (const int*)in(s->o_ad_type);
+    d.ad_loc = (const int*)in(s->o_ad_loc);
+    d.ad_data = (const double*)in(s->o_ad_data); d.ad_n = (int)r->ad_energy.size();
+    d.ed_data = (const double*)in(s->o_ed_data); d.edist_law = s->edist_law;
     // widest union grid of two neighbouring rows (unit-base interpolation)
     s->max_u = 0;
     for (int i = 0; i + 2 <= s->NE; ++i) s->max_u = std::max(s->max_u, s->row_off[i + 2] - s->row_off[i]);
@@ -542,7 +576,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         if (s->has_edist) return fail(c, "ndppgpu: elastic reaction with an energy distribution is not supported");
     }
     k_elastic<<<blocks_for((long long)NE * 32, 128), 128, 0, c->stream>>>(n->dev, n->d_slots.as<SlotDev>(),
-                                                                          n->d_el_ids.as<int>(), (int)n->el_ids.size(),
+                                                                          n->d_el_ids, (int)n->el_ids.size(),
                                                                           d_Ein, NE, d_out);
     if (launch_check(c, "k_elastic")) return 1;
     c->stats.file4_calls += 2LL * NE * (long long)n->el_ids.size();
@@ -631,7 +665,7 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     Timed tm(c, &c->pending_all);
     std::vector<int> ids = n->in_ids;
     TmpBuf d_ids_override;
-    const int* d_ids = n->d_in_ids.as<int>();
+    const int* d_ids = n->d_in_ids;
     if (only_slot >= 0) {
         ids.assign(1, only_slot);
         if (tmp_upload(c, d_ids_override, ids.data(), 1)) return 1;
@@ -993,28 +1027,45 @@ int ndppgpu_convert_distro(void* nuc)
     Timed tm(c, &c->pending_all);
     n->el_ids.clear(); n->in_ids.clear();
     std::vector<SlotDev> devs(n->slots.size());
+    // pass 1: one staging arena for the inputs of every slot, one block for every table
+    Arena A;
+    size_t table_bytes = 0;
     for (size_t i = 0; i < n->slots.size(); ++i) {
         Slot* s = n->slots[i].get();
         if (!s->is_init) continue;
         if (!s->has_adist && !s->has_edist) return fail(c, "No distribution associated with this ScattData object.");
+        layout_slot(n, s, A, table_bytes);
+        if (s->rxn->MT == 2) n->el_ids.push_back((int)i); else n->in_ids.push_back((int)i);
+    }
+    const size_t o_el = A.put(n->el_ids.data(), n->el_ids.size()), o_in = A.put(n->in_ids.data(), n->in_ids.size());
+    if (dev_alloc(c, n->d_arena, A.h.size()) || dev_alloc(c, n->d_tables, table_bytes)) return 1;
+    if (!A.h.empty()) {
+        CK(c, cudaMemcpyAsync(n->d_arena.p, A.h.data(), A.h.size(), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (double)A.h.size();
+    }
+    if (table_bytes) CK(c, cudaMemsetAsync(n->d_tables.p, 0, table_bytes, c->stream));
+    n->d_el_ids = (const int*)(n->d_arena.as<unsigned char>() + o_el);
+    n->d_in_ids = (const int*)(n->d_arena.as<unsigned char>() + o_in);
+    // pass 2: device views and the conversion kernels
+    for (size_t i = 0; i < n->slots.size(); ++i) {
+        Slot* s = n->slots[i].get();
+        if (!s->is_init) continue;
         if (build_slot_device(n, s)) return 1;
         const long long total = (long long)s->dev.total_np * s->dev.M;
         if (s->law == 0 || s->law == 3 || s->law == 9) {
             k_convert_file4<<<blocks_for((long long)s->NE * s->dev.M, 256), 256, 0, c->stream>>>(s->dev, n->d_mu.as<double>());
             if (launch_check(c, "k_convert_file4")) return 1;
         } else {
-            k_convert_file6<<<blocks_for(total, 256), 256, 0, c->stream>>>(s->dev, n->d_mu.as<double>(), s->d_eout.as<double>(),
-                                                                          s->d_pdf.as<double>(), s->d_cdf.as<double>(),
-                                                                          s->d_intt.as<int>());
+            k_convert_file6<<<blocks_for(total, 256), 256, 0, c->stream>>>(s->dev, n->d_mu.as<double>(),
+                                                                          const_cast<double*>(s->dev.eout),
+                                                                          const_cast<double*>(s->dev.pdf),
+                                                                          const_cast<double*>(s->dev.cdf),
+                                                                          const_cast<int*>(s->dev.intt));
             if (launch_check(c, "k_convert_file6")) return 1;
         }
         devs[i] = s->dev;
-        if (s->rxn->MT == 2) n->el_ids.push_back((int)i); else n->in_ids.push_back((int)i);
     }
-    if (upload(c, n->d_slots, devs.data(), devs.size())) return 1;
-    if (upload(c, n->d_el_ids, n->el_ids.data(), n->el_ids.size())) return 1;
-    if (upload(c, n->d_in_ids, n->in_ids.data(), n->in_ids.size())) return 1;
-    CK(c, cudaStreamSynchronize(c->stream));
+    if (upload(c, n->d_slots, devs.data(), devs.size())) return 1;   // synchronises: A and devs may go out of scope
     n->converted = true;
     return 0;
 }
@@ -1028,11 +1079,11 @@ int ndppgpu_nuclide_get_table(void* nuc, int slot, int iE, double* distro, doubl
     if (!s->is_init || !n->converted || iE < 1 || iE > s->NE) return fail(c, "get_table: slot not converted or row out of range");
     CK(c, cudaSetDevice(c->device));
     const int M = n->p.mu_bins, off = s->row_off[iE - 1], NP = s->row_off[iE] - off;
-    if (distro) CK(c, cudaMemcpy(distro, s->d_tab.as<double>() + (size_t)off * M, (size_t)NP * M * sizeof(double), cudaMemcpyDeviceToHost));
-    if (Eouts) CK(c, cudaMemcpy(Eouts, s->d_eout.as<double>() + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
-    if (pdf) CK(c, cudaMemcpy(pdf, s->d_pdf.as<double>() + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
-    if (cdf) CK(c, cudaMemcpy(cdf, s->d_cdf.as<double>() + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
-    if (INTT) CK(c, cudaMemcpy(INTT, s->d_intt.as<int>() + (iE - 1), sizeof(int), cudaMemcpyDeviceToHost));
+    if (distro) CK(c, cudaMemcpy(distro, s->dev.tab + (size_t)off * M, (size_t)NP * M * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Eouts) CK(c, cudaMemcpy(Eouts, s->dev.eout + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
+    if (pdf) CK(c, cudaMemcpy(pdf, s->dev.pdf + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
+    if (cdf) CK(c, cudaMemcpy(cdf, s->dev.cdf + off, NP * sizeof(double), cudaMemcpyDeviceToHost));
+    if (INTT) CK(c, cudaMemcpy(INTT, s->dev.intt + (iE - 1), sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1045,7 +1096,7 @@ int ndppgpu_nuclide_set_table(void* nuc, int slot, int iE, const double* distro)
     if (!s->is_init || !n->converted || iE < 1 || iE > s->NE) return fail(c, "set_table: slot not converted or row out of range");
     CK(c, cudaSetDevice(c->device));
     const int M = n->p.mu_bins, off = s->row_off[iE - 1], NP = s->row_off[iE] - off;
-    CK(c, cudaMemcpy(s->d_tab.as<double>() + (size_t)off * M, distro, (size_t)NP * M * sizeof(double), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(s->dev.tab + (size_t)off * M, distro, (size_t)NP * M * sizeof(double), cudaMemcpyHostToDevice));
     c->stats.h2d_bytes += (double)NP * M * sizeof(double);
     return 0;
 }
@@ -1069,10 +1120,10 @@ int ndppgpu_inelastic_dev(void* nuc, const double* d_Ein, int NE, double* d_inel
 int ndppgpu_elastic(void* nuc, const double* Ein, int NE, double* el_mat)
 {
     Nuclide* n = (Nuclide*)nuc;
+    if (n && NE <= 0) return 0;   // an empty grid: nothing to do, whatever the buffers are
     if (!n || !Ein || !el_mat) return fail(n ? n->ctx : nullptr, "ndppgpu_elastic: null argument");
     Ctx* c = n->ctx;
     CK(c, cudaSetDevice(c->device));
-    if (NE <= 0) return 0;
     TmpBuf d_E, d_out;
     const size_t nout = (size_t)NE * n->G * n->L;
     if (tmp_upload(c, d_E, Ein, (size_t)NE) || tmp_alloc(c, d_out, nout * sizeof(double))) return 1;
@@ -1086,6 +1137,7 @@ int ndppgpu_elastic(void* nuc, const double* Ein, int NE, double* el_mat)
 int ndppgpu_inelastic(void* nuc, const double* Ein, int NE, double* inel_mat, double* nuinel_mat)
 {
     Nuclide* n = (Nuclide*)nuc;
+    if (n && NE <= 0) return 0;
     if (!n || !Ein || !inel_mat) return fail(n ? n->ctx : nullptr, "ndppgpu_inelastic: null argument");
     Ctx* c = n->ctx;
     CK(c, cudaSetDevice(c->device));

@@ -150,7 +150,7 @@ def imbalance(plan: Sequence[Sequence[WorkItem]]) -> float:
 
 def run_plan(my_items: Sequence[WorkItem], all_plans: Sequence[Sequence[WorkItem]],
              open_nuclide: Callable[[int], object], integrate: Callable[[object, WorkItem], "torch.Tensor"],
-             close_nuclide: Callable[[object], None], GL: int, device, dst: int = 0):
+             close_nuclide: Callable[[object], None], GL: int, device, dst: int = 0, timers: Optional[dict] = None):
     """Integrate this rank's items and gather every slab to `dst` with one collective.
 
     open_nuclide(index) -> handle (uploads the tables once per nuclide on this rank);
@@ -162,16 +162,32 @@ def run_plan(my_items: Sequence[WorkItem], all_plans: Sequence[Sequence[WorkItem
 
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    import time
+    tm = timers if timers is not None else {}
+    tm.update(opens=0, open_s=0.0, integrate_s=0.0, pack_s=0.0, gather_s=0.0)
+
+    def lap(key, t0):
+        # host wall time of a phase, device drained first: the phases are separated for the report only
+        if timers is not None:
+            torch.cuda.synchronize(device)
+        tm[key] += time.perf_counter() - t0
+
     slabs = []
     handle, cur = None, None
+    t_all = time.perf_counter()
     for it in my_items:
         if it.nuclide != cur:
             if handle is not None:
                 close_nuclide(handle)
+            t0 = time.perf_counter()
             handle, cur = open_nuclide(it.nuclide), it.nuclide
+            tm["opens"] += 1
+            tm["open_s"] += time.perf_counter() - t0      # uploads + convert_distro (synchronous)
         slabs.append(integrate(handle, it))
     if handle is not None:
         close_nuclide(handle)
+    lap("integrate_s", t_all)
+    tm["integrate_s"] -= tm["open_s"]
 
     # rows of every item, known to all ranks after one small all-reduce (tiles are fractions of grids
     # whose exact length only the owner knows)
@@ -187,6 +203,7 @@ def run_plan(my_items: Sequence[WorkItem], all_plans: Sequence[Sequence[WorkItem
     if world > 1:
         dist.all_reduce(rows, op=dist.ReduceOp.SUM)
     rows_h = rows.tolist()
+    t0 = time.perf_counter()
     per_rank = [sum(rows_h[index[(r, it.nuclide, it.matrix, it.tile)]] for it in all_plans[r]) for r in range(world)]
     pad = max(max(per_rank), 1)
     flat = torch.zeros((pad, GL), dtype=torch.float64, device=device)
@@ -194,11 +211,14 @@ def run_plan(my_items: Sequence[WorkItem], all_plans: Sequence[Sequence[WorkItem
     for s in slabs:
         flat[o:o + s.shape[0]] = s
         o += s.shape[0]
+    lap("pack_s", t0)
+    t0 = time.perf_counter()
     if world > 1:
         parts = [torch.empty_like(flat) for _ in range(world)] if rank == dst else None
         dist.gather(flat, parts, dst=dst)
     else:
         parts = [flat]
+    lap("gather_s", t0)
     if rank != dst:
         return None
     out: Dict[Tuple[int, str], list] = {}

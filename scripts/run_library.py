@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--plan", default="lpt", choices=["lpt", "static"])
     ap.add_argument("--check", type=int, default=1, help="nuclides checked against the CPU oracle on rank 0")
     ap.add_argument("--ne-hi", type=int, default=40000)
+    ap.add_argument("--phases", action="store_true",
+                    help="report host wall time per phase (opens / integrate / pack / gather); drains the device "
+                         "between phases, so use a run without it for the headline number")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -105,7 +108,8 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(lib_stream)
     with torch.cuda.stream(lib_stream):
-        got = library.run_plan(plan[rank], plan, open_nuclide, integrate, close_nuclide, GL, dev)
+        phases = {} if args.phases else None
+        got = library.run_plan(plan[rank], plan, open_nuclide, integrate, close_nuclide, GL, dev, timers=phases)
     e1.record(lib_stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -113,7 +117,9 @@ def main():
     wall = time.perf_counter() - t0
     ms = e0.elapsed_time(e1)
     st = ctx.stats(reset=True)
-    busy = torch.tensor([ms, st["kernel_ms"]], dtype=torch.float64, device=dev)
+    ph = phases or {}
+    busy = torch.tensor([ms, st["kernel_ms"]] + [float(ph.get(k, 0.0)) for k in
+                        ("opens", "open_s", "integrate_s", "pack_s", "gather_s")], dtype=torch.float64, device=dev)
     if world > 1:
         all_busy = [torch.empty_like(busy) for _ in range(world)]
         dist.all_gather(all_busy, busy)
@@ -131,6 +137,9 @@ def main():
                 "evals_per_s": evals / wall,
                 "model_imbalance": {k: library.imbalance(v) for k, v in plans.items()},
                 "measured_imbalance": max(float(b[1]) for b in all_busy) / (sum(float(b[1]) for b in all_busy) / world)}
+        if args.phases:
+            for j, k in enumerate(("opens", "open_s", "integrate_s", "pack_s", "gather_s")):
+                line["phase_" + k + "_per_rank"] = [round(float(b[2 + j]), 4) for b in all_busy]
         # parity of sampled nuclides (assembled on rank 0) against the oracle
         if args.check > 0:
             from oracle import pyoracle
