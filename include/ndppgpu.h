@@ -57,7 +57,10 @@ typedef struct {
     long long sab_columns;
     double file6_cm_ms;      /* CUDA-event time of the dominant kernel (k_file6_cm) alone */
     long long file6_cm_launches;
-    double reserved[6];
+    double host_call_ms;     /* host wall time spent inside the integrator entry points */
+    double host_alloc_ms;    /* ... of which in device allocations (stream-ordered pool) */
+    double host_sync_ms;     /* ... of which blocked on the device (count read-backs, result copies) */
+    double reserved[3];
 } ndppgpu_stats_t;
 
 /* ---- context -------------------------------------------------------------------------------- */

@@ -45,7 +45,8 @@ class StatsC(C.Structure):
                 ("launches", C.c_longlong), ("moment_evals", C.c_longlong), ("file4_calls", C.c_longlong),
                 ("file6_cm_points", C.c_longlong), ("file6_lab_calls", C.c_longlong), ("freegas_tasks", C.c_longlong),
                 ("sab_columns", C.c_longlong), ("file6_cm_ms", C.c_double), ("file6_cm_launches", C.c_longlong),
-                ("reserved", C.c_double * 6)]
+                ("host_call_ms", C.c_double), ("host_alloc_ms", C.c_double), ("host_sync_ms", C.c_double),
+                ("reserved", C.c_double * 3)]
 
 
 _lib = None

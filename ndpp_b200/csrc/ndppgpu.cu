@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +44,18 @@ struct Ctx {
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
     bool f6_solo = false;    // NDPPGPU_F6_SOLO=1: one role per warp on the same tables (A/B measurement)
     bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
+    // file-6 CM scratch (records, sorted flags, materialised unit-base tables): kept for the life of the context
+    // and grown on demand.  cudaMemGetInfo plus a multi-GB pool allocation per call left the GPU idle for most of
+    // a millisecond per work item of a library run; the budget is taken once.
+    void* f6_rec = nullptr; void* f6_sorted = nullptr; void* f6_femu = nullptr;
+    size_t f6_rec_bytes = 0, f6_sorted_bytes = 0, f6_femu_bytes = 0, f6_budget = 0;
+};
+
+struct HostTimer {   // adds the enclosing scope's host wall time to a stats field
+    double* sink;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(double* s) : sink(s), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() { *sink += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 int fail(Ctx* c, const std::string& msg)
@@ -73,6 +86,7 @@ struct DevBuf {  // owning device allocation (stream-ordered pool: no device-wid
 
 int dev_alloc(Ctx* c, DevBuf& b, size_t bytes)
 {
+    HostTimer ht(&c->stats.host_alloc_ms);
     if (b.p) { cudaFreeAsync(b.p, b.st); b.p = nullptr; }
     b.bytes = bytes;
     b.st = c->stream;
@@ -96,6 +110,7 @@ struct TmpBuf {
 
 int tmp_alloc(Ctx* c, TmpBuf& b, size_t bytes)
 {
+    HostTimer ht(&c->stats.host_alloc_ms);
     if (b.p) { cudaFreeAsync(b.p, b.st); b.p = nullptr; }
     b.bytes = bytes;
     b.st = c->stream;
@@ -420,7 +435,10 @@ int check_device_error(Nuclide* n)
     Ctx* c = n->ctx;
     int e = 0;
     CK(c, cudaMemcpyAsync(&e, n->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    {
+        HostTimer ht(&c->stats.host_sync_ms);
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
     if (e != 0) {
         CK(c, cudaMemsetAsync(n->d_err.p, 0, sizeof(int), c->stream));
         return fail(c, "Value outside of array during binary search");
@@ -519,7 +537,19 @@ int launch_file6_ws(Ctx* c, int L, int blocks, const NucDev& nd, const double* d
     }
 }
 
-struct F6WsScratch { TmpBuf rec, sorted, femu, act, n_act, counter; };
+struct F6WsScratch { TmpBuf act, n_act, counter; };
+
+// grow-only device buffer owned by the context (stream-ordered: reuse by later work on the same stream is safe)
+int ctx_scratch(Ctx* c, void*& p, size_t& have, size_t bytes)
+{
+    if (have >= bytes) return 0;
+    HostTimer ht(&c->stats.host_alloc_ms);
+    if (p) CK(c, cudaFreeAsync(p, c->stream));
+    p = nullptr; have = 0;
+    CK(c, cudaMallocAsync(&p, bytes, c->stream));
+    have = bytes;
+    return 0;
+}
 
 // integrate_file6_cm_leg for every active E_in of the call: active list, then per batch of E_in (sized so
 // that the materialised unit-base tables fit the scratch budget) records + tables + the pipeline kernel.
@@ -533,25 +563,35 @@ int file6_cm_ws(Ctx* c, Nuclide* n, Slot* s, const double* d_Ein, int NE, const 
     if (launch_check(c, "k_f6_active")) return 1;
     int n_act = 0;
     CK(c, cudaMemcpyAsync(&n_act, w.n_act.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    {
+        HostTimer ht(&c->stats.host_sync_ms);
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
     if (n_act == 0) return 0;
-    size_t free_b = 0, total_b = 0;
-    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    if (c->f6_budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(c, cudaMemGetInfo(&free_b, &total_b));
+        c->f6_budget = std::min<size_t>((size_t)8 << 30, std::max<size_t>(free_b / 4, (size_t)64 << 20));
+    }
     const size_t per_ein = (size_t)ub.maxU * M * sizeof(double);
-    const size_t budget = std::min<size_t>((size_t)8 << 30, std::max<size_t>(free_b / 4, per_ein));
+    const size_t budget = std::max<size_t>(c->f6_budget, per_ein);
     const int nb = (int)std::min<size_t>({(size_t)n_act, std::max<size_t>(budget / per_ein, 1), (size_t)65535});
-    if (tmp_alloc(c, w.rec, (size_t)nb * ub.maxU * sizeof(UbRec)) || tmp_alloc(c, w.sorted, nb * sizeof(int)) ||
-        tmp_alloc(c, w.femu, (size_t)nb * per_ein))
+    if (ctx_scratch(c, c->f6_rec, c->f6_rec_bytes, (size_t)nb * ub.maxU * sizeof(UbRec)) ||
+        ctx_scratch(c, c->f6_sorted, c->f6_sorted_bytes, nb * sizeof(int)) ||
+        ctx_scratch(c, c->f6_femu, c->f6_femu_bytes, (size_t)nb * per_ein))
         return 1;
+    UbRec* const d_rec = (UbRec*)c->f6_rec;
+    int* const d_sorted = (int*)c->f6_sorted;
+    double* const d_femu = (double*)c->f6_femu;
     for (int a0 = 0; a0 < n_act; a0 += nb) {
         const int na = std::min(nb, n_act - a0);
         CK(c, cudaMemsetAsync(w.counter.p, 0, sizeof(unsigned long long), c->stream));
-        k_f6_records<<<na, 128, 0, c->stream>>>(ub, w.act.as<int>(), a0, w.rec.as<UbRec>(), w.sorted.as<int>());
+        k_f6_records<<<na, 128, 0, c->stream>>>(ub, w.act.as<int>(), a0, d_rec, d_sorted);
         if (launch_check(c, "k_f6_records")) return 1;
         k_f6_femu<<<dim3(blocks_for(M, 256), ub.maxU, na), 256, 0, c->stream>>>(n->dev, s->dev, ub, w.act.as<int>(), a0,
-                                                                                w.femu.as<double>());
+                                                                                d_femu);
         if (launch_check(c, "k_f6_femu")) return 1;
-        F6WsArgs a{w.rec.as<UbRec>(), w.sorted.as<int>(), w.femu.as<double>(), n->d_rmu.as<double>(), w.act.as<int>(),
+        F6WsArgs a{d_rec, d_sorted, d_femu, n->d_rmu.as<double>(), w.act.as<int>(),
                    a0, na, w.counter.as<unsigned long long>()};
         const long long pairs = (long long)na * G;
         const int blocks = (int)std::min<long long>((long long)F6_BLOCKS_PER_SM * c->sm_count,
@@ -567,6 +607,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
     Ctx* c = n->ctx;
     if (require_converted(n)) return 1;
     if (NE <= 0) return 0;
+    HostTimer hcall(&c->stats.host_call_ms);
     const int GL = n->G * n->L;
     Timed tm(c, &c->pending_all);
     for (int sid : n->el_ids) {
@@ -656,6 +697,7 @@ int inelastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out, double
     Ctx* c = n->ctx;
     if (require_converted(n)) return 1;
     if (NE <= 0) return 0;
+    HostTimer hcall(&c->stats.host_call_ms);
     const int G = n->G, L = n->L, GL = G * L, M = n->p.mu_bins;
     const size_t nslots = n->slots.size();
     std::vector<const double*> pre(nslots, nullptr);
@@ -854,6 +896,7 @@ int ndppgpu_finalize(void* ctx)
     cudaStreamSynchronize(c->stream);
     for (auto& p : c->pending_all) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->pending_f6) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (void* p : {c->f6_rec, c->f6_sorted, c->f6_femu}) if (p) cudaFree(p);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

@@ -74,11 +74,16 @@ def main():
         grids[i] = (Eel, Einel)
         return (dn, Eel_d, Ein_d)
 
-    def integrate(h, it):
+    def rows_of(it):
+        _, Eel, Einel = parsed[it.nuclide]
+        lo, hi = library.tile_bounds(len(Eel if it.matrix == "el" else Einel), it.tile, it.n_tiles)
+        return hi - lo
+
+    def integrate(h, it, out):
         dn, Eel_d, Ein_d = h
         E = Eel_d if it.matrix == "el" else Ein_d
         lo, hi = library.tile_bounds(E.numel(), it.tile, it.n_tiles)
-        out = torch.empty((hi - lo, GL), dtype=torch.float64, device=dev)
+        assert out.shape[0] == hi - lo
         if hi > lo:
             if it.matrix == "el":
                 dn.elastic_dev(E[lo:hi], out)
@@ -109,7 +114,8 @@ def main():
     e0.record(lib_stream)
     with torch.cuda.stream(lib_stream):
         phases = {} if args.phases else None
-        got = library.run_plan(plan[rank], plan, open_nuclide, integrate, close_nuclide, GL, dev, timers=phases)
+        got = library.run_plan(plan[rank], plan, open_nuclide, integrate, close_nuclide, GL, dev, timers=phases,
+                               rows_of=rows_of)
     e1.record(lib_stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -119,7 +125,8 @@ def main():
     st = ctx.stats(reset=True)
     ph = phases or {}
     busy = torch.tensor([ms, st["kernel_ms"]] + [float(ph.get(k, 0.0)) for k in
-                        ("opens", "open_s", "integrate_s", "pack_s", "gather_s")], dtype=torch.float64, device=dev)
+                        ("opens", "open_s", "integrate_s", "pack_s", "gather_s")] +
+                        [st["host_call_ms"], st["host_alloc_ms"], st["host_sync_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         all_busy = [torch.empty_like(busy) for _ in range(world)]
         dist.all_gather(all_busy, busy)
@@ -137,6 +144,8 @@ def main():
                 "evals_per_s": evals / wall,
                 "model_imbalance": {k: library.imbalance(v) for k, v in plans.items()},
                 "measured_imbalance": max(float(b[1]) for b in all_busy) / (sum(float(b[1]) for b in all_busy) / world)}
+        for j, k in enumerate(("host_call_ms", "host_alloc_ms", "host_sync_ms")):
+            line[k + "_per_rank"] = [round(float(b[7 + j]), 1) for b in all_busy]
         if args.phases:
             for j, k in enumerate(("opens", "open_s", "integrate_s", "pack_s", "gather_s")):
                 line["phase_" + k + "_per_rank"] = [round(float(b[2 + j]), 4) for b in all_busy]

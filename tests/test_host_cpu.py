@@ -228,6 +228,21 @@ def integrate(i, it):               # stand-in for the device integration: rows 
     return out
 got = library.run_plan(plan[rank], plan, open_nuclide, integrate, lambda h: None, GL, torch.device("cpu"))
 assert len(opened) == len(set(opened)), "a nuclide was opened twice on one rank"
+opened.clear()
+# the in-place form (heights from the host-side grids, one result buffer per rank) assembles the same library
+def rows_of(it):
+    lo, hi = library.tile_bounds(len(grids[it.nuclide][0 if it.matrix == "el" else 1]), it.tile, it.n_tiles)
+    return hi - lo
+def integrate_into(i, it, out):
+    out.copy_(integrate(i, it))
+got2 = library.run_plan(plan[rank], plan, open_nuclide, integrate_into, lambda h: None, GL, torch.device("cpu"),
+                        rows_of=rows_of)
+if rank == 0:
+    assert set(got2) == set(got)
+    for key in got:
+        a = torch.cat([p[2] for p in sorted(got[key], key=lambda p: p[0])])
+        b = torch.cat([p[2] for p in sorted(got2[key], key=lambda p: p[0])])
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)), key
 if rank == 0:
     assert set(got) == {(s.index, m) for s in shapes for m in ("el", "inel")}
     for (i, m), pieces in got.items():
