@@ -60,7 +60,8 @@ typedef struct {
     double host_call_ms;     /* host wall time spent inside the integrator entry points */
     double host_alloc_ms;    /* ... of which in device allocations (stream-ordered pool) */
     double host_sync_ms;     /* ... of which blocked on the device (count read-backs, result copies) */
-    double reserved[3];
+    long long freegas_items; /* work items the free-gas sub-integrals were cut into (all generations) */
+    double reserved[2];
 } ndppgpu_stats_t;
 
 /* ---- context -------------------------------------------------------------------------------- */

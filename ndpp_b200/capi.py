@@ -46,7 +46,7 @@ class StatsC(C.Structure):
                 ("file6_cm_points", C.c_longlong), ("file6_lab_calls", C.c_longlong), ("freegas_tasks", C.c_longlong),
                 ("sab_columns", C.c_longlong), ("file6_cm_ms", C.c_double), ("file6_cm_launches", C.c_longlong),
                 ("host_call_ms", C.c_double), ("host_alloc_ms", C.c_double), ("host_sync_ms", C.c_double),
-                ("reserved", C.c_double * 3)]
+                ("freegas_items", C.c_longlong), ("reserved", C.c_double * 2)]
 
 
 _lib = None

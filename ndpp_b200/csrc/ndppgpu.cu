@@ -42,6 +42,8 @@ struct Ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
     int sm_count = 148;
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
+    int fg_split_depth = 2;  // NDPPGPU_FG_SPLIT: levels of the outer recursion one work item walks (1..4); C3: 506 / 485 / 455 / 452 ms at 4 / 3 / 2 / 1
+    long long fg_queue_cap = 0;               // NDPPGPU_FG_QUEUE: first-attempt capacity of the item queue (tests)
     bool f6_solo = false;    // NDPPGPU_F6_SOLO=1: one role per warp on the same tables (A/B measurement)
     bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
     // file-6 CM scratch (records, sorted flags, materialised unit-base tables): kept for the life of the context
@@ -648,37 +650,83 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             k_fg_tasks<<<blocks_for(tasks, 256), 256, 0, c->stream>>>(n->dev, d_Ein, idx.as<int>(), n_idx,
                                                                        d_tasks.as<int>(), d_heads.as<int>());
             if (launch_check(c, "k_fg_tasks")) return 1;
-            // persistent warps with their level-parallel scratch.  The worst case of the inner recursion is a
-            // frontier of 2^its intervals (2^(its+1) nodes); real integrals stay far below, so the first attempt
-            // runs with 4096 / 32768 per warp (NDPPGPU_FG_CAP overrides, for the tests) and the kernel flags an overflow, in which case the call is
-            // repeated with the worst-case sizes.
+            // Persistent warps with their level-parallel scratch.  The worst case of the inner recursion is a
+            // frontier of 2^its intervals (2^(its+1) nodes); real integrals stay far below, so the first attempt runs
+            // with 4096 / 32768 per warp (NDPPGPU_FG_CAP overrides, for the tests).  The outer recursion is cut into
+            // items of bounded size that are processed generation by generation (kernels_freegas.cuh); the item
+            // queue and its token arena start from an estimate.  The kernels flag either overflow, in which case
+            // the call is repeated with the worst-case scratch / a queue four times as large.
             cudaDeviceProp prop;
             CK(c, cudaGetDeviceProperties(&prop, c->device));
-            const int blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * FG_BLOCKS_PER_SM,
-                                                        (tasks + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
-            const size_t warps = (size_t)blocks * FG_WARPS_PER_BLOCK, full = (size_t)1 << n->p.adaptive_mu_its;
-            TmpBuf d_ovf;
-            if (tmp_alloc(c, d_ovf, sizeof(int))) return 1;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                const size_t capF = attempt ? full : std::min<size_t>(full, (size_t)c->fg_first_cap);
-                const size_t capN = attempt ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap);
+            const long long n_root = tasks * rows;
+            const int max_blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * FG_BLOCKS_PER_SM,
+                                                            (n_root + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
+            const size_t warps = (size_t)max_blocks * FG_WARPS_PER_BLOCK, full = (size_t)1 << n->p.adaptive_mu_its;
+            TmpBuf d_ovf, d_items, d_ival, d_roff, d_rlen, d_ops, d_pay, d_tails;
+            if (tmp_alloc(c, d_ovf, sizeof(int)) || tmp_alloc(c, d_tails, 2 * sizeof(unsigned long long))) return 1;
+            bool worst_scratch = false;
+            long long cap_items = std::min<long long>(std::max<long long>(8 * n_root, 1LL << 20), 1LL << 25);
+            if (c->fg_queue_cap > 0) cap_items = c->fg_queue_cap;
+            for (int attempt = 0;; ++attempt) {
+                const size_t capF = worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap);
+                const size_t capN = worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap);
+                const long long cap_tok = 4 * cap_items + 64;
+                const long long n_all = n_root + cap_items;
                 if (tmp_alloc(c, d_frames, warps * 2 * capF * sizeof(FgFrame)) ||
-                    tmp_alloc(c, d_nvals, warps * capN * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)))
+                    tmp_alloc(c, d_nvals, warps * capN * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
+                    tmp_alloc(c, d_items, (size_t)cap_items * sizeof(FgItem)) || tmp_alloc(c, d_ival, (size_t)n_all * sizeof(double)) ||
+                    tmp_alloc(c, d_roff, (size_t)n_all * sizeof(long long)) || tmp_alloc(c, d_rlen, (size_t)n_all * sizeof(int)) ||
+                    tmp_alloc(c, d_ops, (size_t)cap_tok) || tmp_alloc(c, d_pay, (size_t)cap_tok * sizeof(double)))
                     return 1;
                 CK(c, cudaMemsetAsync(d_ovf.p, 0, sizeof(int), c->stream));
-                CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
-                k_freegas_warp<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
-                    n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, d_tasks.as<int>(), tasks,
-                    d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
-                    (int)capF, (int)capN, d_ovf.as<int>(), raw.as<double>());
-                if (launch_check(c, "k_freegas_warp")) return 1;
+                CK(c, cudaMemsetAsync(d_tails.p, 0, 2 * sizeof(unsigned long long), c->stream));
+                FgQueue q{};
+                q.tasks = d_tasks.as<int>(); q.n_root = n_root; q.items = d_items.as<FgItem>(); q.cap_items = cap_items;
+                q.tail = d_tails.as<unsigned long long>(); q.tok_tail = q.tail + 1;
+                q.ival = d_ival.as<double>(); q.roff = d_roff.as<long long>(); q.rlen = d_rlen.as<int>();
+                q.ops = d_ops.as<unsigned char>(); q.pay = d_pay.as<double>(); q.cap_tok = cap_tok;
+                q.split_depth = c->fg_split_depth; q.overflow = d_ovf.as<int>();
+                std::vector<long long> bounds{0, n_root};   // generation g = items [bounds[g], bounds[g+1])
                 int ovf = 0;
-                CK(c, cudaMemcpyAsync(&ovf, d_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-                CK(c, cudaStreamSynchronize(c->stream));
-                if (!ovf || (capF == full && capN == 2 * full)) {
-                    if (ovf) return fail(c, "ndppgpu: free-gas recursion outgrew its worst-case scratch");
-                    break;
+                for (;;) {
+                    const long long lo = bounds[bounds.size() - 2], hi = bounds.back();
+                    const int blocks = (int)std::min<long long>(max_blocks, (hi - lo + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
+                    CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
+                    k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
+                        n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q, lo, hi,
+                        d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
+                        (int)capF, (int)capN, d_ovf.as<int>());
+                    if (launch_check(c, "k_freegas_items")) return 1;
+                    unsigned long long tails[2] = {0, 0};
+                    CK(c, cudaMemcpyAsync(tails, d_tails.p, sizeof(tails), cudaMemcpyDeviceToHost, c->stream));
+                    CK(c, cudaMemcpyAsync(&ovf, d_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    CK(c, cudaStreamSynchronize(c->stream));
+                    if (ovf) break;
+                    const long long new_hi = n_root + (long long)tails[0];
+                    if (new_hi == hi) break;
+                    if (bounds.size() > (size_t)n->p.adaptive_eout_its + 3)
+                        return fail(c, "ndppgpu: free-gas item generations did not terminate");
+                    bounds.push_back(new_hi);
                 }
+                if (ovf) {
+                    if (attempt >= 6) return fail(c, "ndppgpu: free-gas recursion outgrew its scratch");
+                    if (ovf & 1) {
+                        if (worst_scratch) return fail(c, "ndppgpu: free-gas recursion outgrew its worst-case scratch");
+                        worst_scratch = true;
+                    }
+                    if (ovf & 2) cap_items *= 4;
+                    continue;
+                }
+                // items that referred to later generations: evaluate their programs, last generation first
+                for (int g = (int)bounds.size() - 3; g >= 0; --g) {
+                    const long long lo = bounds[g], hi = bounds[g + 1];
+                    k_fg_combine<<<blocks_for(hi - lo, 256), 256, 0, c->stream>>>(q, lo, hi);
+                    if (launch_check(c, "k_fg_combine")) return 1;
+                }
+                k_fg_store<<<blocks_for(n_root, 256), 256, 0, c->stream>>>(q, rows, n->G, n->L, raw.as<double>());
+                if (launch_check(c, "k_fg_store")) return 1;
+                c->stats.freegas_items += bounds.back();
+                break;
             }
             k_freegas_finish<<<blocks_for((long long)n_idx * 32, 128), 128, 0, c->stream>>>(
                 n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, raw.as<double>(), d_out);
@@ -875,6 +923,10 @@ int ndppgpu_init(int device, void** ctx)
         c->f6_legacy = e && e[0] == '1';
         e = std::getenv("NDPPGPU_FG_CAP");
         if (e && std::atoi(e) >= 2) c->fg_first_cap = std::atoi(e);
+        e = std::getenv("NDPPGPU_FG_SPLIT");
+        if (e && std::atoi(e) >= 1) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
+        e = std::getenv("NDPPGPU_FG_QUEUE");
+        if (e && std::atoll(e) >= 2) c->fg_queue_cap = std::atoll(e);
         e = std::getenv("NDPPGPU_F6_SOLO");
         c->f6_solo = e && e[0] == '1';
     }

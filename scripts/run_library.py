@@ -56,7 +56,7 @@ def main():
     G, L, M, K = 70, 6, params.mu_bins, params.ne_per_grp
     GL = G * L
     shapes = [synth.c5_shape(s) for s in specs]
-    items = library.make_items(shapes, G, L, M, K, tile_rows=args.tile_rows)
+    items = library.make_items(shapes, G, L, M, K, tile_rows=args.tile_rows, world=world)
     plans = {"lpt": library.plan_lpt(items, world), "static": library.plan_static_blocks(items, shapes, world)}
     plan = plans[args.plan]
     spec_of = {s[0]: s for s in specs}

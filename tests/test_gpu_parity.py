@@ -460,4 +460,29 @@ def test_freegas_scratch_overflow_reruns_with_worst_case_sizes(scatt, monkeypatc
         dn.clear()
         outs.append(launches)
     assert np.array_equal(outs[0], outs[2]) and np.any(outs[0] != 0)
-    assert outs[3] == outs[1] + 1        # one extra k_freegas_warp launch
+    assert outs[3] > outs[1]             # the generations were launched again
+
+
+def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
+    """The outer recursion is cut into work items of `split` levels that are processed generation by generation and
+    re-assembled by their postfix programs: the moments must not depend on the cut, and a queue that is too small
+    must be detected and the pass repeated with a larger one."""
+    from ndpp_b200.capi import Context
+    nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=1000)
+    Ein = Ein[[0, 450, 900]]
+    outs, items = [], []
+    for split, queue in (("4", None), ("3", None), ("2", None), ("1", None), ("2", "512")):
+        monkeypatch.setenv("NDPPGPU_FG_SPLIT", split)
+        if queue is None:
+            monkeypatch.delenv("NDPPGPU_FG_QUEUE", raising=False)
+        else:
+            monkeypatch.setenv("NDPPGPU_FG_QUEUE", queue)
+        ctx = Context(-1)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        outs.append(dn.elastic(Ein))
+        items.append(ctx.stats()["freegas_items"])
+        dn.clear()
+    assert np.any(outs[0] != 0)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+    assert items[0] < items[1] < items[2] < items[3] and items[4] == items[2]
