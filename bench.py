@@ -173,7 +173,7 @@ def cpu_run(nuc, e_bins, params, Ein_el, Ein_inel, n_sample, threads, seed=0):
     total = dt + t_conv * frac
     desc = (f"{len(s_el)} of {len(Ein_el)} elastic + {len(s_in)} of {len(Ein_inel)} inelastic E_in (every "
             f"{max(1, int(round(1 / frac)))}th point, shuffled, dynamic chunk 1), {threads} OpenMP threads, "
-            f"oracle = C restatement of the reference (gcc -O2, no FMA contraction)")
+            f"oracle = C restatement of the reference (gcc -O3, no FMA contraction)")
     return ev / total, total, desc
 
 

@@ -672,7 +672,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 const size_t capN = worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap);
                 const long long cap_tok = 4 * cap_items + 64;
                 const long long n_all = n_root + cap_items;
-                if (tmp_alloc(c, d_frames, warps * 2 * capF * sizeof(FgFrame)) ||
+                if (tmp_alloc(c, d_frames, warps * 2 * (capF / 2) * sizeof(FgPair) + sizeof(FgPair)) ||
                     tmp_alloc(c, d_nvals, warps * capN * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
                     tmp_alloc(c, d_items, (size_t)cap_items * sizeof(FgItem)) || tmp_alloc(c, d_ival, (size_t)n_all * sizeof(double)) ||
                     tmp_alloc(c, d_roff, (size_t)n_all * sizeof(long long)) || tmp_alloc(c, d_rlen, (size_t)n_all * sizeof(int)) ||
@@ -694,7 +694,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                     CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
                     k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
                         n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q, lo, hi,
-                        d_counter.as<unsigned long long>(), d_frames.as<FgFrame>(), d_nvals.as<double>(), d_nchilds.as<int>(),
+                        d_counter.as<unsigned long long>(), d_frames.as<FgPair>(), d_nvals.as<double>(), d_nchilds.as<int>(),
                         (int)capF, (int)capN, d_ovf.as<int>());
                     if (launch_check(c, "k_freegas_items")) return 1;
                     unsigned long long tails[2] = {0, 0};

@@ -104,7 +104,11 @@ def main():
     wd.inelastic_dev(wE, wo)
     wd.clear()
     if world > 1:
+        # NCCL sets up its all-reduce rings and its point-to-point connections lazily, on the first collective of
+        # each kind: one small all-reduce and one small gather before the clock starts
         dist.all_reduce(torch.zeros(1, device=dev))
+        w_flat = torch.zeros((4, GL), dtype=torch.float64, device=dev)
+        dist.gather(w_flat, [torch.empty_like(w_flat) for _ in range(world)] if rank == 0 else None, dst=0)
     ctx.stats(reset=True)
     torch.cuda.synchronize()
     if world > 1:
