@@ -665,7 +665,8 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             TmpBuf d_ovf, d_items, d_ival, d_roff, d_rlen, d_ops, d_pay, d_tails;
             if (tmp_alloc(c, d_ovf, sizeof(int)) || tmp_alloc(c, d_tails, 2 * sizeof(unsigned long long))) return 1;
             bool worst_scratch = false;
-            long long cap_items = std::min<long long>(std::max<long long>(8 * n_root, 1LL << 20), 1LL << 25);
+            // measured on C3: 1.40e6 sub-integrals hand on 1.4e5 items at 2 levels per item (3e5 at 1 level)
+            long long cap_items = std::max<long long>(n_root / 2, 1LL << 18);
             if (c->fg_queue_cap > 0) cap_items = c->fg_queue_cap;
             for (int attempt = 0;; ++attempt) {
                 const size_t capF = worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap);
