@@ -4,6 +4,8 @@
   reference_kats.json   the known-answer vectors the reference's own test program holds for this path
                         (transcribed, with their file:line; the Fortran itself cannot be run here -- no
                         Fortran compiler in the image)
+  chi_vectors.npz       oracle outputs of the fission-spectrum integration (calc_chi) on the two synthetic
+                        fissionable nuclides, merged grid and a dense grid
   oracle_vectors.npz    outputs of the pinned CPU oracle (oracle/, checked against the KATs by
                         tests/test_oracle_golden.py) on small seeded inputs of every integrator, for the
                         GPU parity tests and as a guard against the oracle drifting
@@ -101,8 +103,27 @@ def vectors():
     return out
 
 
+def chi_vectors():
+    from ndpp_b200 import synth
+    from oracle import pyoracle
+    out = {}
+    e_bins = synth.group_structure(70)
+    dense = np.geomspace(1e-11, 20.0, 97)
+    for name, mk in (("total", synth.fissile_total), ("partial", synth.fissile_partial)):
+        for gname, grid in (("merged", None), ("dense", dense)):
+            E, t, p, d = pyoracle.calc_chi(mk(), e_bins, E_grid=grid)
+            out[f"{name}_{gname}_E"], out[f"{name}_{gname}_total"] = E, t
+            out[f"{name}_{gname}_prompt"], out[f"{name}_{gname}_delay"] = p, d
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    cv = chi_vectors()
+    np.savez_compressed(os.path.join(GOLD, "chi_vectors.npz"), **cv)
+    if "--chi-only" in sys.argv:
+        print({k: getattr(a, "shape", None) for k, a in cv.items()})
+        sys.exit(0)
     json.dump(KATS, open(os.path.join(GOLD, "reference_kats.json"), "w"), indent=1)
     v = vectors()
     np.savez_compressed(os.path.join(GOLD, "oracle_vectors.npz"), **v)

@@ -184,3 +184,33 @@ def test_gpu_chi_quirks_and_errors(oracle):
     nuc.nu_t_type = 0
     with pytest.raises(ValueError, match="No neutron emission data"):
         hostchi.calc_chi(nuc, E_BINS)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/chi_vectors.npz, written by scripts/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _chi_gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chi_vectors.npz"))
+
+
+def test_chi_oracle_reproduces_committed_vectors(oracle):
+    v = _chi_gold()
+    for name, mk in (("total", synth.fissile_total), ("partial", synth.fissile_partial)):
+        for gname in ("merged", "dense"):
+            E, t, p, d = oracle.calc_chi(mk(), E_BINS, E_grid=v[f"{name}_{gname}_E"])
+            # exp / erf of the host libm sit between input and output: last-bit differences between machines allowed
+            assert np.allclose(t, v[f"{name}_{gname}_total"], rtol=1e-13, atol=1e-16, equal_nan=True)
+            assert np.allclose(p, v[f"{name}_{gname}_prompt"], rtol=1e-13, atol=1e-16, equal_nan=True)
+            assert np.allclose(d, v[f"{name}_{gname}_delay"], rtol=1e-13, atol=1e-16, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gpu_chi_against_committed_vectors():
+    v = _chi_gold()
+    for name, mk in (("total", synth.fissile_total), ("partial", synth.fissile_partial)):
+        for gname in ("merged", "dense"):
+            E, t, p, d = hostchi.calc_chi(mk(), E_BINS, E_grid=v[f"{name}_{gname}_E"])
+            _same(t, v[f"{name}_{gname}_total"], f"golden chi_total {name} {gname}")
+            _same(p, v[f"{name}_{gname}_prompt"], f"golden chi_prompt {name} {gname}")
+            _same(d, v[f"{name}_{gname}_delay"], f"golden chi_delay {name} {gname}")
