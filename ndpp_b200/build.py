@@ -35,5 +35,23 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     return SO
 
 
+TOOL_SRC = os.path.join(os.path.dirname(HERE), "tools", "ndpp_calc_scatt.cpp")
+TOOL = os.path.join(os.path.dirname(HERE), "tools", "ndpp_calc_scatt")
+
+
+def build_tool(force: bool = False) -> str:
+    """The C++ driver above the C-ABI (tools/ndpp_calc_scatt.cpp over include/ndpp_host.hpp), linked against the
+    in-tree libndppgpu.so with an $ORIGIN-relative rpath so that the pair travels to the GPU box."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    deps = [TOOL_SRC, os.path.join(inc, "ndpp_host.hpp"), os.path.join(inc, "ndppgpu.h"), SO]
+    if not force and os.path.exists(TOOL) and all(os.path.getmtime(d) <= os.path.getmtime(TOOL) for d in deps):
+        return TOOL
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", inc, TOOL_SRC, "-o", TOOL, "-L", CSRC,
+           "-lndppgpu", "-Wl,-rpath,$ORIGIN/../ndpp_b200/csrc"]
+    subprocess.check_call(cmd)
+    return TOOL
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else [])
+    build_tool(force=True)

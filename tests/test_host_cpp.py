@@ -1,0 +1,140 @@
+"""The C++ host layer above the C-ABI (include/ndpp_host.hpp, tools/ndpp_calc_scatt.cpp): calc_scatt and
+calc_scattsab with the reference's argument lists, driven from a compiled program as the reference's
+preprocess_ndpp drives the Fortran routines.  CPU: it builds with -Wall -Wextra, links against libndppgpu.so,
+and fails loudly the way fatal_error does.  GPU: its moments equal the oracle's (BASELINE tolerance) and the
+Python mirror's bit for bit (both are thin callers of the same library)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ndpp_b200 import ace, dump, synth
+from ndpp_b200 import build as nbuild
+from tests.util import assert_parity, assert_parity_floor, small_heavy
+
+
+@pytest.fixture(scope="module")
+def tool():
+    nbuild.build()
+    return nbuild.build_tool()
+
+
+def _run(tool, case, res, expect_ok=True):
+    r = subprocess.run([tool, str(case), str(res)], capture_output=True, text=True, timeout=600)
+    if expect_ok:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def test_tool_builds_and_links_the_c_abi(tool):
+    assert os.access(tool, os.X_OK)
+    out = subprocess.run(["ldd", tool], capture_output=True, text=True).stdout
+    assert "libndppgpu.so" in out and "not found" not in out.split("libndppgpu.so")[1].splitlines()[0]
+
+
+def test_fatal_error_convention(tool, tmp_path):
+    # src/error.F90:79-154: " ERROR: <message>" on stderr, non-zero status
+    r = _run(tool, tmp_path / "missing.case", tmp_path / "x.res", expect_ok=False)
+    assert r.returncode != 0 and r.stderr.startswith(" ERROR: Cannot open case file")
+    bad = tmp_path / "bad.case"
+    np.array([7.0, 1.0]).astype("<f8").tofile(bad)
+    r = _run(tool, bad, tmp_path / "x.res", expect_ok=False)
+    assert r.returncode != 0 and r.stderr.startswith(" ERROR: ")
+
+
+def test_no_cpu_fallback_without_a_gpu(tool, tmp_path):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    nuc, e_bins, params = synth.c1_fixture()
+    Ein = synth.c1_ein_grid(13)
+    dump.write_nuclide_case(tmp_path / "c1.case", nuc, e_bins, params.scatt_type, params.order, params.mu_bins, True,
+                            Ein, Ein, params)
+    r = _run(tool, tmp_path / "c1.case", tmp_path / "c1.res", expect_ok=False)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr and not os.path.exists(tmp_path / "c1.res")
+
+
+def test_case_file_round_trip_layout(tmp_path):
+    """The case file is the flat argument list: its length follows from the fields (guards the C++ reader's
+    field order against the writer's)."""
+    nuc, e_bins, params = synth.c1_fixture()
+    Ein = synth.c1_ein_grid(5)
+    p = tmp_path / "c1.case"
+    dump.write_nuclide_case(p, nuc, e_bins, 0, 5, 3001, False, Ein, None, params)
+    a = np.fromfile(p, dtype="<f8")
+    assert a[0] == dump.KIND_NUCLIDE and a[1] == nuc.awr and a[4] == len(nuc.energy)
+    assert a[-1] == 0.0 and np.array_equal(a[-1 - len(Ein):-1], Ein) and a[-2 - len(Ein)] == len(Ein)
+
+
+@pytest.mark.gpu
+def test_cpp_calc_scatt_c1(tool, oracle, tmp_path):
+    from ndpp_b200 import scatt
+    nuc, e_bins, params = synth.c1_fixture()
+    Ein = synth.c1_ein_grid(40)
+    Ein_inel = Ein[Ein >= 2.0]
+    dump.write_nuclide_case(tmp_path / "c1.case", nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, True, Ein, Ein_inel,
+                            params)
+    r = _run(tool, tmp_path / "c1.case", tmp_path / "c1.res")
+    assert "moment evaluations" in r.stdout
+    el, inel, nu = dump.read_result(tmp_path / "c1.res")
+    pel, pinel, pnu = scatt.calc_scatt(nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, True, Ein, Ein_inel)
+    assert np.array_equal(el, pel) and np.array_equal(inel, pinel) and np.array_equal(nu, pnu)
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=5, mu_bins=3001, nuscatter=True))
+    rn.convert_distro()
+    assert_parity(el, rn.elastic(Ein), what="C++ calc_scatt C1 elastic")
+    ri, rnu = rn.inelastic(Ein_inel)
+    assert_parity_floor(inel, ri, what="C++ calc_scatt C1 inelastic")
+    assert_parity_floor(nu, rnu, what="C++ calc_scatt C1 nu-inelastic")
+    # nuscatt = .false. and no inelastic grid: the two matrices stay unallocated (src/scatt.F90:146-150)
+    dump.write_nuclide_case(tmp_path / "c1b.case", nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, False, Ein, None, params)
+    _run(tool, tmp_path / "c1b.case", tmp_path / "c1b.res")
+    el2, inel2, nu2 = dump.read_result(tmp_path / "c1b.res")
+    assert inel2 is None and nu2 is None and np.array_equal(el2, el)
+
+
+@pytest.mark.gpu
+def test_cpp_calc_scatt_heavy_shape(tool, oracle, tmp_path):
+    nuc = small_heavy()
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=7, mu_bins=2001, nuscatter=True)
+    rng = np.random.default_rng(11)
+    Ein = np.sort(np.exp(rng.uniform(np.log(1e-10), np.log(19.9), 60)))
+    Ein_inel = Ein[Ein >= 0.05]
+    dump.write_nuclide_case(tmp_path / "h.case", nuc, e_bins, params.scatt_type, params.order, params.mu_bins, True,
+                            Ein, Ein_inel, params)
+    _run(tool, tmp_path / "h.case", tmp_path / "h.res")
+    el, inel, nu = dump.read_result(tmp_path / "h.res")
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    assert_parity(el, rn.elastic(Ein), what="C++ calc_scatt heavy elastic")
+    ri, rnu = rn.inelastic(Ein_inel)
+    assert_parity_floor(inel, ri, what="C++ calc_scatt heavy inelastic")
+    assert_parity_floor(nu, rnu, what="C++ calc_scatt heavy nu-inelastic")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,elastic", [("skewed", None), ("cont", "incoherent")])
+def test_cpp_calc_scattsab(tool, oracle, tmp_path, mode, elastic):
+    sab = synth.c4_sab(mode=mode, elastic=elastic, n_ein=30)
+    e_bins = synth.group_structure(70)
+    rng = np.random.default_rng(5)
+    Ein = np.sort(np.concatenate([sab.inelastic_e_in, np.exp(rng.uniform(np.log(1e-11), np.log(4e-6), 100)), [5e-6]]))
+    dump.write_sab_case(tmp_path / "s.case", sab, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 2001, Ein)
+    _run(tool, tmp_path / "s.case", tmp_path / "s.res")
+    got, _, _ = dump.read_result(tmp_path / "s.res")
+    assert_parity(got, oracle.sab_calc(sab, e_bins, 5, Ein), what=f"C++ calc_scattsab {mode}")
+
+
+@pytest.mark.gpu
+def test_cpp_fatal_error_carries_the_reference_message(tool, tmp_path):
+    nuc, e_bins, params = synth.c1_fixture()
+    # E_in above the last tabulated adist energy: the reference aborts in binary_search (src/search.F90:36-38)
+    dump.write_nuclide_case(tmp_path / "e.case", nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, False,
+                            np.array([1.5]), np.array([2.7]), params)
+    r = _run(tool, tmp_path / "e.case", tmp_path / "e.res", expect_ok=False)
+    assert r.returncode != 0 and r.stderr.startswith(" ERROR: ") and "binary search" in r.stderr
+    assert not os.path.exists(tmp_path / "e.res")
