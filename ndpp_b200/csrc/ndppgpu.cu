@@ -32,7 +32,7 @@ using namespace ndpp;
 
 namespace {
 
-std::string g_last_error;
+thread_local std::string g_last_error;  // context-less failures (ndppgpu_init), per calling thread
 
 struct Ctx {
     int device = 0;
@@ -140,6 +140,8 @@ template <class T> int upload(Ctx* c, DevBuf& b, const T* h, size_t n)
     return 0;
 }
 
+void fold_events(Ctx* c, bool only_completed);
+
 struct Timed {  // CUDA-event bracket on the context stream, resolved lazily in ndppgpu_stats
     Ctx* c;
     cudaEvent_t a = nullptr, b = nullptr;
@@ -154,8 +156,26 @@ struct Timed {  // CUDA-event bracket on the context stream, resolved lazily in 
     {
         cudaEventRecord(b, c->stream);
         sink->push_back({a, b});
+        // a caller that never asks for ndppgpu_stats (the Fortran driver) must not accumulate events without bound
+        if (sink->size() >= 1024) fold_events(c, /*only_completed=*/true);
     }
 };
+
+void fold_events(Ctx* c, bool only_completed)
+{
+    auto fold = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double& acc) {
+        size_t keep = 0;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (only_completed && cudaEventQuery(v[i].second) != cudaSuccess) { v[keep++] = v[i]; continue; }
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, v[i].first, v[i].second) == cudaSuccess) acc += ms;
+            cudaEventDestroy(v[i].first); cudaEventDestroy(v[i].second);
+        }
+        v.resize(keep);
+    };
+    fold(c->pending_all, c->stats.kernel_ms);
+    fold(c->pending_f6, c->stats.file6_cm_ms);
+}
 
 // ---- reaction / slot bookkeeping ---------------------------------------------------------------
 struct HostRxn {
@@ -974,20 +994,7 @@ int ndppgpu_stats(void* ctx, ndppgpu_stats_t* out, int reset)
     if (!c) return fail(nullptr, "ndppgpu_stats: null ctx");
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
-    for (auto& p : c->pending_all) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, p.first, p.second);
-        c->stats.kernel_ms += ms;
-        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
-    }
-    c->pending_all.clear();
-    for (auto& p : c->pending_f6) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, p.first, p.second);
-        c->stats.file6_cm_ms += ms;
-        cudaEventDestroy(p.first); cudaEventDestroy(p.second);
-    }
-    c->pending_f6.clear();
+    fold_events(c, /*only_completed=*/false);
     if (out) *out = c->stats;
     if (reset) std::memset(&c->stats, 0, sizeof(c->stats));
     return 0;
