@@ -161,9 +161,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #define F6_STAGES (1 << F6_STAGE_BITS)
 #define F6_CONS 4
 #define F6_THREADS ((F6_NPROD + 1) * 128)
-// Measured on B200 (C2, k_file6_cm 203 ms): 1 producer per consumer, 2 blocks/SM -> 183 ms; 2 producers with
+// Measured on B200 (C2, k_file6_cm 203 ms): 1 producer per consumer, 2 blocks/SM -> 173-183 ms; 2 producers with
 // setmaxnreg 56/128 -> 189 ms; 3 producers, 1 block/SM -> 238 ms.
-#define F6_BLOCKS_PER_SM (F6_NPROD == 1 ? 2 : 1)
+// Occupancy and the register split (C2, same box, kernel ms): 2 blocks/SM at 128 registers 172.6;
+// 3 blocks/SM at 80 registers 169.8; 3 blocks/SM with the producers handing registers to the consumers
+// (setmaxnreg 64/96: 170.2, 56/104: 168.0, 48/112: 169.1, 40/120: 172.7); 4 blocks/SM 64/64: 181.7, 40/88: 174.2.
+// With the fused closed forms (legendre_fused.inc), whose live ranges are shorter: 56/104: 160.2, 64/96: 161.3,
+// 48/112: 164.8; 4 blocks/SM 40/88: 166.7, 48/80: 165.4.
+#ifndef F6_BLOCKS_PER_SM
+#define F6_BLOCKS_PER_SM (F6_NPROD == 1 ? 3 : 1)
+#endif
+// setmaxnreg budgets of the two warpgroups.  They must balance against the launch allocation, 65536 / (256 * 3) rounded
+// down to a multiple of 8 = 80 registers: 128 * (80 - 56) == 128 * (104 - 80); an unbalanced pair deadlocks.
+#if F6_NPROD == 1 && F6_BLOCKS_PER_SM == 3 && !defined(F6_REG_PROD) && !defined(F6_NO_SETMAXNREG)
+#define F6_REG_PROD 56
+#define F6_REG_CONS 104
+#endif
 
 struct F6Shared {
     double buf[F6_CONS][F6_NPROD][F6_STAGES][32];
@@ -338,6 +351,9 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
 #define F6_TASK_ADVANCE() do { if (++tslot == 2) { tslot = 0; tphase ^= 1u; } } while (0)
 
     if (producer) {
+#ifdef F6_REG_PROD
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F6_REG_PROD));
+#endif
         double* const ring = &sh.buf[cons][q][0][0];
         const uint32_t full0 = smem_u32(&sh.full[cons][q][0]), empty0 = smem_u32(&sh.empty[cons][q][0]);
         int stage = 0;
@@ -387,6 +403,9 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
             }
         }
     } else {
+#ifdef F6_REG_CONS
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F6_REG_CONS));
+#endif
         // ring positions of the F6_NPROD producers, packed: F6_STAGE_BITS of stage + 1 bit of phase each
         uint32_t pos = 0;
         const uint32_t full00 = smem_u32(&sh.full[cons][0][0]), empty00 = smem_u32(&sh.empty[cons][0][0]);

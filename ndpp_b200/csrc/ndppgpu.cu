@@ -480,7 +480,18 @@ __global__ void k_test_legendre(int n, int L, const double* __restrict__ xl, con
     Powers A, B;
     make_powers(xl[i], A);
     make_powers(xh[i], B);
-    add_int_pn_tablelin(L, xl[i], xh[i], fl[i], fh[i], A, B, acc);
+    // even inputs take the run-time-order path (the reference text), odd inputs the compile-time-order path the hot
+    // kernels use (legendre_fused.inc): the parity test holds both against the oracle
+    if ((i & 1) == 0) add_int_pn_tablelin(L, xl[i], xh[i], fl[i], fh[i], A, B, acc);
+    else {
+        switch (L) {
+#define NDPP_CASE(N) case N: add_int_pn_tablelin<N>(N, xl[i], xh[i], fl[i], fh[i], A, B, acc); break;
+        NDPP_CASE(1) NDPP_CASE(2) NDPP_CASE(3) NDPP_CASE(4) NDPP_CASE(5) NDPP_CASE(6) NDPP_CASE(7) NDPP_CASE(8)
+        NDPP_CASE(9) NDPP_CASE(10) NDPP_CASE(11)
+#undef NDPP_CASE
+        default: break;
+        }
+    }
     calc_pn_all(L, xl[i], p);
     for (int l = 0; l < L; ++l) { integ[(size_t)i * L + l] = acc[l]; pn[(size_t)i * L + l] = p[l]; }
 }

@@ -265,3 +265,20 @@ def test_library_run_plan_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_LIB_OK" in out.stdout
+
+
+def test_fused_closed_forms_are_current_and_bit_identical_on_the_host():
+    """csrc/legendre_fused.inc (an off-by-default variant of the closed-form Legendre integrals with the exact
+    power-of-two scalings folded into FMAs) is regenerated from the reference text in
+    csrc/legendre.cuh and compared bit for bit with the oracle on the host."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_legendre_fused", os.path.join(root, "scripts", "gen_legendre_fused.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    text, marks = g.generate()
+    assert open(g.OUT).read() == text, "legendre_fused.inc is stale"
+    assert marks[7] < 330          # L = 8: 291 FP64 operations against 330 of the text as written
+    rc, msg = g.check(300000)
+    assert rc == 0 and msg.endswith(" 0 mismatches"), msg
