@@ -156,7 +156,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #define F6_NPROD 1
 #endif
 #ifndef F6_STAGE_BITS
-#define F6_STAGE_BITS 3   // ring of 2^bits windows per producer; A/B on C2 (one run each): 4 stages 183-189 ms, 8: 182.6, 16: 174.5, 32: 181.1 -- inside the run-to-run noise
+#define F6_STAGE_BITS 3   // ring of 2^bits windows per producer; A/B on C2 at 3 blocks/SM (same box, +-0.3 ms): 4 stages 161.0 ms, 8: 160.3, 16: 161.8
 #endif
 #define F6_STAGES (1 << F6_STAGE_BITS)
 #define F6_CONS 4
