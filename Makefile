@@ -14,7 +14,7 @@ all: $(LIB) $(TOOL) oracle
 $(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.inc) include/ndppgpu.h
 	$(NVCC) $(NVCCFLAGS) $(NDPP_NVCC_EXTRA) -o $@ $(CSRC)/ndppgpu.cu
 
-$(TOOL): tools/ndpp_calc_scatt.cpp include/ndpp_host.hpp include/ndppgpu.h $(LIB)
+$(TOOL): tools/ndpp_calc_scatt.cpp include/ndpp_host.hpp include/ndpp_library.hpp include/ndppgpu.h $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -I include $< -o $@ -L $(CSRC) -lndppgpu '-Wl,-rpath,$$ORIGIN/../ndpp_b200/csrc'
 
 oracle:

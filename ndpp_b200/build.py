@@ -43,7 +43,7 @@ def build_tool(force: bool = False) -> str:
     """The C++ driver above the C-ABI (tools/ndpp_calc_scatt.cpp over include/ndpp_host.hpp), linked against the
     in-tree libndppgpu.so with an $ORIGIN-relative rpath so that the pair travels to the GPU box."""
     inc = os.path.join(os.path.dirname(HERE), "include")
-    deps = [TOOL_SRC, os.path.join(inc, "ndpp_host.hpp"), os.path.join(inc, "ndppgpu.h"), SO]
+    deps = [TOOL_SRC, os.path.join(inc, "ndpp_host.hpp"), os.path.join(inc, "ndpp_library.hpp"), os.path.join(inc, "ndppgpu.h"), SO]
     if not force and os.path.exists(TOOL) and all(os.path.getmtime(d) <= os.path.getmtime(TOOL) for d in deps):
         return TOOL
     cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", inc, TOOL_SRC, "-o", TOOL, "-L", CSRC,

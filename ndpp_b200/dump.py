@@ -111,6 +111,19 @@ def write_sab_case(path, sab: SAlphaBeta, energy_bins, scatt_type, order, mu_bin
     o.save(path)
 
 
+def write_result(path, el, inel=None, nu=None, kind=KIND_NUCLIDE):
+    """The result-file layout of tools/ndpp_calc_scatt.cpp, from [NE][G][L] arrays (used to feed its library writer)."""
+    el = np.asarray(el, dtype=np.float64)
+    _, G, L = el.shape
+    ne_in = 0 if inel is None else len(inel)
+    parts = [np.array([kind, len(el), G, L, ne_in, 0.0 if nu is None else 1.0]), el.ravel()]
+    if inel is not None:
+        parts.append(np.asarray(inel, dtype=np.float64).ravel())
+    if nu is not None:
+        parts.append(np.asarray(nu, dtype=np.float64).ravel())
+    np.concatenate(parts).astype("<f8").tofile(path)
+
+
 def read_result(path):
     """(el_mat, inel_mat, nuinel_mat) as [NE][G][L] arrays (None where the reference leaves them unallocated);
     for an S(a,b) case el_mat is scatt_mat."""

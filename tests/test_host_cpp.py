@@ -70,6 +70,87 @@ def test_case_file_round_trip_layout(tmp_path):
     assert a[-1] == 0.0 and np.array_equal(a[-1 - len(Ein):-1], Ein) and a[-2 - len(Ein)] == len(Ein)
 
 
+def _library_case(tmp_path, nus, inel, three_digit_exponent=False):
+    """C1 nuclide header + made-up matrices with leading / trailing zero groups and an all-zero column."""
+    rng = np.random.default_rng(42)
+    nuc, e_bins, params = synth.c1_fixture()
+    G, L = len(e_bins) - 1, 6
+    Eel = np.geomspace(1e-9, 2.9, 23)
+    Einel = np.geomspace(2.0, 3.003, 9) if inel else None
+
+    def mat(NE):
+        m = rng.normal(size=(NE, G, L)) * 0.1
+        m[:, :, 0] = np.abs(m[:, :, 0])
+        m[1] = 0.0                      # an all-zero column: gmin = gmax = 0
+        m[2, 1:, :] = 0.0               # trailing zero group
+        m[3, 0, :] = 0.0                # leading zero group
+        if three_digit_exponent:
+            m[4, 0, 1] = -3.25e-123
+            m[5, 1, 2] = 7.5e+104
+        return m
+    el = mat(len(Eel))
+    inm = mat(len(Einel)) if inel else None
+    nu = mat(len(Einel)) if (inel and nus) else None
+    dump.write_nuclide_case(tmp_path / "lib.case", nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, nus, Eel, Einel, params)
+    dump.write_result(tmp_path / "lib.res", el, inm, nu)
+    return nuc, e_bins, Eel, el, Einel, inm, nu
+
+
+@pytest.mark.parametrize("fmt", ["binary", "ascii"])
+@pytest.mark.parametrize("nus,inel", [(True, True), (False, True), (False, False)])
+def test_cpp_library_writer_matches_the_python_writer_byte_for_byte(tool, tmp_path, fmt, nus, inel):
+    """include/ndpp_library.hpp (init_library + print_scatt) against ndpp_b200/output.py, which tests/test_output.py
+    holds against the reference's own reader."""
+    from ndpp_b200 import output
+    nuc, e_bins, Eel, el, Einel, inm, nu = _library_case(tmp_path, nus, inel, three_digit_exponent=(fmt == "ascii"))
+    cpp, py = tmp_path / f"cpp.{fmt}", tmp_path / f"py.{fmt}"
+    cmd = [tool, str(tmp_path / "lib.case"), str(tmp_path / "lib.res"), "--library-only", "--library", str(cpp),
+           "--name", "92238.71c", "--thin-tol", "0.002"] + (["--ascii"] if fmt == "ascii" else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    with output.LibraryWriter(str(py), "92238.71c", nuc.kT, e_bins, 0, 5, nus, 3001, 0.002, fmt) as w:
+        w.print_scatt(Eel, el, Einel, inm, nu)
+    assert open(cpp, "rb").read() == open(py, "rb").read()
+    if fmt == "binary":
+        lib = output.read_library(str(cpp))
+        assert lib["trailing_bytes"] == 0 and lib["name"] == "92238.71c " and lib["NG"] == len(e_bins) - 1
+        assert np.array_equal(lib["Ein_el"], Eel) and (lib["Ein_inel"] is None) == (not inel)
+
+
+def test_cpp_library_writer_rejects_a_mismatched_result(tool, tmp_path):
+    _library_case(tmp_path, False, True)
+    dump.write_result(tmp_path / "lib.res", np.zeros((3, 2, 6)))
+    r = subprocess.run([tool, str(tmp_path / "lib.case"), str(tmp_path / "lib.res"), "--library-only", "--library",
+                        str(tmp_path / "x.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and r.stderr.startswith(" ERROR: Result file does not match")
+
+
+@pytest.mark.gpu
+def test_cpp_driver_writes_the_library_the_python_driver_writes(tool, tmp_path):
+    """calc_scatt + apply_tol_scatt + thin_grid + init_library + print_scatt from the C++ driver (src/ndpp.F90:560-702)
+    against ndpp_b200.driver.preprocess_nuclide: the same device calls, so the files must be identical."""
+    from ndpp_b200 import driver, output
+    nuc = small_heavy()
+    nuc.name = "92238.71c"
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=5, mu_bins=2001, nuscatter=True)
+    rng = np.random.default_rng(12)
+    Ein = np.sort(np.exp(rng.uniform(np.log(1e-10), np.log(19.9), 300)))
+    Ein_inel = Ein[Ein >= 0.05]
+    dump.write_nuclide_case(tmp_path / "d.case", nuc, e_bins, params.scatt_type, params.order, params.mu_bins, True,
+                            Ein, Ein_inel, params)
+    for fmt, flag in (("binary", []), ("ascii", ["--ascii"])):
+        cpp, py = tmp_path / f"cpp.{fmt}", tmp_path / f"py.{fmt}"
+        r = subprocess.run([tool, str(tmp_path / "d.case"), str(tmp_path / "d.res"), "--library", str(cpp), "--name",
+                            nuc.name, "--print-tol", "1e-8", "--thin-tol", "0.002"] + flag,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        res = driver.preprocess_nuclide(nuc, e_bins, params, print_tol=1e-8, thin_tol=0.002, Ein_el=Ein,
+                                        Ein_inel=Ein_inel, library_file=str(py), lib_format=fmt)
+        assert len(res.Ein_el) <= len(Ein)
+        assert open(cpp, "rb").read() == open(py, "rb").read()
+
+
 @pytest.mark.gpu
 def test_cpp_calc_scatt_c1(tool, oracle, tmp_path):
     from ndpp_b200 import scatt

@@ -4,6 +4,13 @@
 // (src/ndpp.F90:607-609, 773-775) and writes the moment arrays to a result file.
 //
 //   ndpp_calc_scatt CASE RESULT [--device N]
+//                   [--library FILE [--ascii] [--name ZAID] [--print-tol P] [--thin-tol T]]   nuclide cases only
+//                   [--library-only]
+//
+// With --library the program does what the per-nuclide body of preprocess_ndpp does (src/ndpp.F90:560-702):
+// calc_scatt, apply_tol_scatt and thin_grid in one device call per matrix set (ndppgpu_*_thinned), then init_library
+// and print_scatt (include/ndpp_library.hpp).  --library-only skips the integration and writes the library from the
+// matrices of an existing RESULT file on the grids of CASE (no GPU needed: used by the CPU tests of the writer).
 //
 // Errors end the program the way the reference's fatal_error does (src/error.F90:79-154): " ERROR: <message>"
 // on stderr and a non-zero exit status.  All arithmetic runs in libndppgpu.so; there is no CPU path.
@@ -15,6 +22,7 @@
 #include <vector>
 
 #include "ndpp_host.hpp"
+#include "ndpp_library.hpp"
 
 using namespace ndpp_host;
 
@@ -88,7 +96,33 @@ void write_result(const char* path, double kind, int G, int L, const std::vector
     if (!ok) fatal_error(std::string("Cannot write result file ") + path);
 }
 
-void run_nuclide(const Context& ctx, Reader& r, const char* out)
+struct Options {
+    int device = -1;
+    std::string library, name = "synthetic";
+    bool ascii = false, library_only = false;
+    double print_tol = 1.0e-8, thin_tol = 0.0;   // print_tol default of src/constants.F90; thin_tol as a fraction
+};
+
+// the matrices of a RESULT file written by write_result
+void read_result(const char* path, int G, int L, std::vector<double>& el, std::vector<double>& inel,
+                 std::vector<double>& nu)
+{
+    Reader r(path);
+    r.num();
+    const int ne_el = r.inum(), g = r.inum(), l = r.inum(), ne_in = r.inum(), has_nu = r.inum();
+    if (g != G || l != L) fatal_error("Result file does not match the case (groups / orders)");
+    const size_t w = (size_t)G * L;
+    auto take = [&](size_t n, std::vector<double>& v) {
+        if (r.pos + n > r.a.size()) fatal_error("Result file ends early");
+        v.assign(r.a.begin() + r.pos, r.a.begin() + r.pos + n);
+        r.pos += n;
+    };
+    take(ne_el * w, el);
+    take(ne_in * w, inel);
+    if (has_nu) take(ne_in * w, nu); else nu.clear();
+}
+
+void run_nuclide(const Context* ctx, Reader& r, const char* out, const Options& opt)
 {
     Nuclide nuc;
     nuc.awr = r.num(); nuc.kT = r.num(); nuc.freegas_cutoff = r.num();
@@ -126,10 +160,37 @@ void run_nuclide(const Context& ctx, Reader& r, const char* out)
     const std::vector<double> Ein_el = r.vec(), Ein_inel = r.vec();
 
     std::vector<double> el_mat, inel_mat, nuinel_mat;
-    calc_scatt(ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, Ein_el, Ein_inel, el_mat, inel_mat,
-               nuinel_mat, st);
     const int L = (scatt_type == SCATT_TYPE_LEGENDRE) ? order + 1 : order;
-    write_result(out, KIND_NUCLIDE, (int)energy_bins.size() - 1, L, el_mat, inel_mat, nuinel_mat);
+    const int G = (int)energy_bins.size() - 1;
+    std::vector<double> xe = Ein_el, xi = Ein_inel;   // the grids that end up in the library
+    if (opt.library_only) {
+        read_result(out, G, L, el_mat, inel_mat, nuinel_mat);
+        if (el_mat.size() != xe.size() * (size_t)G * L || inel_mat.size() != xi.size() * (size_t)G * L)
+            fatal_error("Result file does not match the grids of the case");
+    } else if (!opt.library.empty()) {
+        // src/ndpp.F90:607-648 with the tolerance and the thinning on the device; tokeep = the group edges (:641-648)
+        double compr = 0.0, err = 0.0;
+        ScattDataSet rxn_data(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
+        rxn_data.calc_elastic_thinned(xe, opt.print_tol, opt.thin_tol, energy_bins, el_mat, compr, err);
+        if (!xi.empty())
+            rxn_data.calc_inelastic_thinned(xi, nuscatt, opt.print_tol, opt.thin_tol, energy_bins, inel_mat, nuinel_mat,
+                                            compr, err);
+        rxn_data.clear();
+        write_result(out, KIND_NUCLIDE, G, L, el_mat, inel_mat, nuinel_mat);
+    } else {
+        calc_scatt(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, Ein_el, Ein_inel, el_mat, inel_mat,
+                   nuinel_mat, st);
+        write_result(out, KIND_NUCLIDE, G, L, el_mat, inel_mat, nuinel_mat);
+    }
+    if (!opt.library.empty()) {
+        if (scatt_type != SCATT_TYPE_LEGENDRE)
+            fatal_error("Tabular scattering of ACE nuclides is NOT YET IMPLEMENTED");   // as the reference, scattdata_header.F90:1452-1460
+        LibraryWriter w(opt.library, opt.name, nuc.kT, energy_bins, scatt_type, order, nuscatt, mu_bins, opt.thin_tol,
+                        opt.ascii ? LibFormat::ASCII : LibFormat::BINARY);
+        w.print_scatt(xe, el_mat, xi, inel_mat, nuinel_mat);
+        w.close();
+        if (!w.ok()) fatal_error("Cannot write library file " + opt.library);
+    }
 }
 
 void run_sab(const Context& ctx, Reader& r, const char* out)
@@ -159,22 +220,43 @@ void run_sab(const Context& ctx, Reader& r, const char* out)
 int main(int argc, char** argv)
 {
     try {
-        if (argc < 3) fatal_error("usage: ndpp_calc_scatt CASE RESULT [--device N]");
-        int device = -1;
-        for (int i = 3; i + 1 < argc; ++i)
-            if (!std::strcmp(argv[i], "--device")) device = std::atoi(argv[i + 1]);
+        const char* usage = "usage: ndpp_calc_scatt CASE RESULT [--device N] [--library FILE [--ascii] [--name ZAID] "
+                            "[--print-tol P] [--thin-tol T]] [--library-only]";
+        if (argc < 3) fatal_error(usage);
+        Options opt;
+        for (int i = 3; i < argc; ++i) {
+            const std::string a = argv[i];
+            auto value = [&]() -> const char* { if (i + 1 >= argc) fatal_error(usage); return argv[++i]; };
+            if (a == "--device") opt.device = std::atoi(value());
+            else if (a == "--library") opt.library = value();
+            else if (a == "--name") opt.name = value();
+            else if (a == "--print-tol") opt.print_tol = std::atof(value());
+            else if (a == "--thin-tol") opt.thin_tol = std::atof(value());
+            else if (a == "--ascii") opt.ascii = true;
+            else if (a == "--library-only") opt.library_only = true;
+            else fatal_error(usage);
+        }
+        if (opt.library_only && opt.library.empty()) fatal_error(usage);
         Reader r(argv[1]);
         const double kind = r.num();
-        Context ctx(device);
-        if (kind == KIND_NUCLIDE) run_nuclide(ctx, r, argv[2]);
-        else if (kind == KIND_SAB) run_sab(ctx, r, argv[2]);
-        else fatal_error("Case file: unknown kind");
+        if (opt.library_only) {   // the writer alone: no device context
+            if (kind != KIND_NUCLIDE) fatal_error("--library-only needs a nuclide case");
+            run_nuclide(nullptr, r, argv[2], opt);
+            if (r.pos != r.a.size()) fatal_error("Case file has trailing data");
+            return 0;
+        }
+        Context ctx(opt.device);
+        if (kind == KIND_NUCLIDE) run_nuclide(&ctx, r, argv[2], opt);
+        else if (kind == KIND_SAB) {
+            if (!opt.library.empty()) fatal_error("--library is implemented for nuclide cases");
+            run_sab(ctx, r, argv[2]);
+        } else fatal_error("Case file: unknown kind");
         if (r.pos != r.a.size()) fatal_error("Case file has trailing data");
         const ndppgpu_stats_t s = ctx.stats();
         std::printf(" %lld moment evaluations, %lld kernel launches, %.3f ms on the device\n", s.moment_evals,
                     s.launches, s.kernel_ms);
         return 0;
-    } catch (const FatalError& e) {
+    } catch (const std::runtime_error& e) {   // FatalError and the library writer's errors
         std::fprintf(stderr, " ERROR: %s\n", e.what());
         return 255;  // the reference's default error code is -1
     }
