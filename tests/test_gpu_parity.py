@@ -486,3 +486,17 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
     assert items[0] < items[1] < items[2] < items[3] and items[4] == items[2]
+
+
+def test_unitbase_and_file6_cm_leg_heavy_target_limit(scatt, oracle):
+    """The CUDA path against closed forms where the reference holds no test (unit-base interpolation +
+    integrate_file6_cm_leg, A -> infinity, separable tables; tests/util.py: heavy_limit_law61), and against the oracle."""
+    from tests.util import assert_heavy_limit, heavy_limit_law61
+    nuc, e_bins, params, emax = heavy_limit_law61()
+    dn, rn = _pair(scatt, oracle, nuc, e_bins, params)
+    Ein = np.array([1.0, 1.3, 2.0, 2.5, 3.0])
+    got, _ = dn.inelastic(Ein)
+    ref, _ = rn.inelastic(Ein)
+    assert_parity(got, ref, what="heavy-target Law 61")
+    for i, E in enumerate(Ein):
+        assert_heavy_limit(got[i], e_bins, float(emax(E)))

@@ -365,3 +365,15 @@ def test_thin_grid_properties(oracle):
                 assert np.all(np.abs(t - m[k]) / m[k] <= 2e-3 * (1 + 1e-12))
         assert 0.0 < mabs and maxerr >= 0.0
     assert len(oracle.thin_grid(x, y, tokeep, 2e-3, y2)[0]) >= len(oracle.thin_grid(x, y, tokeep, 2e-3)[0])
+
+
+@pytest.mark.parametrize("Ein", [1.0, 2.0, 2.5, 3.0])
+def test_unitbase_and_file6_cm_leg_heavy_target_limit(oracle, Ein):
+    """No reference test exists for unit-base interpolation and integrate_file6_cm_leg (parity unpinned): here the
+    restatement is held against closed forms in the A -> infinity limit (tests/util.py: heavy_limit_law61)."""
+    from tests.util import assert_heavy_limit, heavy_limit_law61
+    nuc, e_bins, params, emax = heavy_limit_law61()
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    inel, _ = rn.inelastic(np.array([Ein]))
+    assert_heavy_limit(inel[0], e_bins, float(emax(Ein)))

@@ -37,3 +37,50 @@ def small_heavy(n_grid=400, n_levels=6, seed=7, **kw):
     from ndpp_b200 import synth
     return synth.heavy_nuclide(n_grid=n_grid, n_levels=n_levels, seed=seed, n_ein_cont=8, np_cont=12, n_el_adist=12,
                                n_lvl_adist=6, np_lvl=9, **kw)
+
+
+def heavy_limit_law61(b=0.6, awr=1.0e8, NP=41):
+    """Analytic pin of unit-base interpolation + integrate_file6_cm_leg (src/scattdata_header.F90:1521-1717, 1085-1266),
+    for which the reference holds no test: one CM continuum reaction (Law 61) on an infinitely heavy target, so that
+    CM = lab (c -> 0, J -> 1), whose tables are separable -- pdf(E_out) = 2 E / Emax^2 on [0, Emax] (Emax = 0.8 at
+    E_in = 1, 2.0 at E_in = 3: unit-base interpolation gives the same triangle on the interpolated Emax) times the
+    angular density 0.5 (1 + b mu) (P0 = 1, P1 = b/3, higher moments 0).  sigma = p_valid = 1, so the inelastic matrix is
+    the normalised distribution itself.  Returns (nuclide, energy_bins, params, Emax(E_in))."""
+    from ndpp_b200 import ace
+    e_in, emax = np.array([1.0, 3.0]), np.array([0.8, 2.0])
+    blocks, locs = [], []
+    pos = 2 + 2 * len(e_in)
+    for Em in emax:
+        Eout = np.linspace(0.0, Em, NP)
+        ang = [np.array([2.0, 2.0, -1.0, 1.0, 0.5 * (1 - b), 0.5 * (1 + b), 0.0, 1.0]) for _ in range(NP)]
+        LC = pos + 2 + 4 * NP + 8.0 * np.arange(NP)
+        locs.append(pos)
+        blocks.append(np.concatenate([[2.0, float(NP)], Eout, 2.0 * Eout / Em ** 2, Eout ** 2 / Em ** 2, LC] + ang))
+        pos += 2 + 4 * NP + 8 * NP
+    data = np.concatenate([[0.0, float(len(e_in))], e_in, np.asarray(locs, float)] + blocks)
+    energy = np.geomspace(1e-3, 20.0, 60)
+    rxn = ace.Reaction(MT=91, Q_value=-0.1, threshold=1, scatter_in_cm=True, sigma=np.ones(len(energy)),
+                       edist=ace.DistEnergy(law=61, data=data,
+                                            p_valid=ace.Tab1(x=np.array([energy[0], 20.0]), y=np.array([1.0, 1.0]))))
+    nuc = ace.Nuclide(awr=awr, kT=0.0, energy=energy, elastic=np.ones(len(energy)),
+                      reactions=[ace.Reaction(MT=2, threshold=1), rxn])
+    e_bins = np.array([0.0, 0.2, 0.5, 0.9, 1.4, 5.0])
+    return nuc, e_bins, ace.Params(order=3, mu_bins=201), (lambda E: np.interp(E, e_in, emax))
+
+
+def assert_heavy_limit(m, e_bins, Emax, b=0.6):
+    """m[g][l] at one E_in against the closed forms of heavy_limit_law61."""
+    assert abs(m[:, 0].sum() - 1.0) < 1e-12                      # normalised to sum_g P0 = 1 (:1255-1264)
+    edges = np.minimum(e_bins, Emax)
+    p0 = (edges[1:] ** 2 - edges[:-1] ** 2) / Emax ** 2
+    inside = np.nonzero(e_bins[1:] < Emax)[0]                    # groups wholly below the kinematic edge
+    assert len(inside) >= 2
+    # the trapezoid over the NE_PER_GRP outgoing energies is exact for the linear pdf, so interior groups are in the
+    # analytic ratio; the group that holds Emax loses part of its last interval (the integrand drops to zero within
+    # 1e-8 of Emax), an inherent feature of the reference's quadrature: checked to 2 %
+    assert np.allclose(m[inside, 0] / m[inside[0], 0], p0[inside] / p0[inside[0]], rtol=1e-6)
+    assert np.allclose(m[:, 0], p0, atol=0.02)
+    assert np.allclose(m[inside, 1] / m[inside, 0], b / 3.0, rtol=1e-6)
+    assert np.all(np.abs(m[inside, 2:] / m[inside, :1]) < 1e-6)
+    above = np.nonzero(e_bins[:-1] >= Emax)[0]
+    assert np.all(np.abs(m[above, 0]) < 1e-6)                    # nothing beyond the unit-base interpolated Emax
