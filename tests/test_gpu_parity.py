@@ -500,3 +500,16 @@ def test_unitbase_and_file6_cm_leg_heavy_target_limit(scatt, oracle):
     assert_parity(got, ref, what="heavy-target Law 61")
     for i, E in enumerate(Ein):
         assert_heavy_limit(got[i], e_bins, float(emax(E)))
+
+
+def test_freegas_p0_matches_the_analytic_kernel_for_A1(scatt):
+    """The CUDA free-gas path against the closed-form A = 1 kernel (tests/util.py: freegas_a1_analytic_p0)."""
+    from tests.util import freegas_a1_analytic_p0
+    nuc, eb, params, _ = synth.c3_h1_freegas(n_ein=8)
+    nuc.awr = 1.0
+    dn = scatt.DeviceNuclide(nuc, eb, params)
+    xs = np.array([0.3, 2.0, 10.0, 60.0])
+    got = dn.elastic(xs * nuc.kT)
+    for i, x in enumerate(xs):
+        p = freegas_a1_analytic_p0(x * nuc.kT, nuc.kT, eb)
+        assert np.abs(got[i, :, 0] - p).max() < 5e-6, x

@@ -377,3 +377,20 @@ def test_unitbase_and_file6_cm_leg_heavy_target_limit(oracle, Ein):
     rn.convert_distro()
     inel, _ = rn.inelastic(np.array([Ein]))
     assert_heavy_limit(inel[0], e_bins, float(emax(Ein)))
+
+
+@pytest.mark.parametrize("x", [0.3, 2.0, 10.0, 60.0])
+def test_freegas_p0_matches_the_analytic_kernel_for_A1(oracle, x):
+    """The reference holds no test for freegas.F90 (parity unpinned).  For A = 1, constant sigma and isotropic CM
+    scattering the free-gas kernel has a closed form: the restatement's group probabilities must reproduce it to the
+    tolerance of the reference's own adaptive quadrature (1e-7 in mu, 1e-8 in E_out: measured 1e-8 .. 2e-6)."""
+    from tests.util import freegas_a1_analytic_p0
+    nuc, eb, params, _ = synth.c3_h1_freegas(n_ein=8)
+    nuc.awr = 1.0
+    rn = oracle.RefNuclide(nuc, eb, params)
+    rn.convert_distro()
+    E = x * nuc.kT
+    m = rn.elastic(np.array([E]))[0]
+    p = freegas_a1_analytic_p0(E, nuc.kT, eb)
+    assert abs(p.sum() - 1.0) < 1e-9
+    assert np.abs(m[:, 0] - p).max() < 5e-6

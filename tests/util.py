@@ -84,3 +84,22 @@ def assert_heavy_limit(m, e_bins, Emax, b=0.6):
     assert np.all(np.abs(m[inside, 2:] / m[inside, :1]) < 1e-6)
     above = np.nonzero(e_bins[:-1] >= Emax)[0]
     assert np.all(np.abs(m[above, 0]) < 1e-6)                    # nothing beyond the unit-base interpolated Emax
+
+
+def freegas_a1_analytic_p0(E, kT, e_bins):
+    """Group probabilities of the free-gas scattering kernel of a target of mass ratio A = 1 with a constant,
+    isotropic-in-CM cross section (the closed form of e.g. Bell & Glasstone, Nuclear Reactor Theory, section 7.3:
+    sigma(E -> E') E = erf(sqrt(E'/kT)) for E' < E and exp((E - E')/kT) erf(sqrt(E/kT)) for E' > E, with
+    sigma_s(E) = (1 + kT/2E) erf(sqrt(E/kT)) + exp(-E/kT) / sqrt(pi E/kT)), integrated over every group with scipy."""
+    from scipy import integrate, special
+    x = E / kT
+
+    def kern(xp):
+        return special.erf(np.sqrt(xp)) if xp < x else np.exp(x - xp) * special.erf(np.sqrt(x))
+    sig = (1.0 + 0.5 / x) * special.erf(np.sqrt(x)) + np.exp(-x) / np.sqrt(np.pi * x)
+    p = np.zeros(len(e_bins) - 1)
+    for g in range(len(p)):
+        lo, hi = e_bins[g] / kT, e_bins[g + 1] / kT
+        p[g] = integrate.quad(kern, lo, hi, points=[x] if lo < x < hi else None, epsabs=1e-14, epsrel=1e-12,
+                              limit=400)[0] / (x * sig)
+    return p
