@@ -394,3 +394,57 @@ def test_freegas_p0_matches_the_analytic_kernel_for_A1(oracle, x):
     p = freegas_a1_analytic_p0(E, nuc.kT, eb)
     assert abs(p.sum() - 1.0) < 1e-9
     assert np.abs(m[:, 0] - p).max() < 5e-6
+
+
+@pytest.mark.parametrize("Ein", [1.2, 3.3, 9.0, 20.0])
+def test_law9_matches_numerical_integration_of_the_evaporation_spectrum(oracle, Ein):
+    """law9_scatter_lab_leg (src/scattdata_header.F90:1274-1326) has no reference test (parity unpinned): its group
+    probabilities are the integrals of E' exp(-E'/T) up to E - U, checked here by numerical quadrature, and its
+    angular moments those of the laboratory angular table (linear: P1/P0 = b/3, higher moments 0)."""
+    from scipy import integrate
+    b = 0.45
+    energy = np.geomspace(1e-11, 20.0, 80)
+    thr = int(np.searchsorted(energy, 1.0)) + 1
+    e0 = energy[thr - 1]
+    e9, T9, U = np.array([e0, 5.0, 20.0]), np.array([0.3, 0.6, 1.1]), 0.4
+    d9 = np.concatenate([[0.0, 3.0], e9, T9, [U]])
+    blk = np.array([2.0, 2.0, -1.0, 1.0, 0.5 * (1 - b), 0.5 * (1 + b), 0.0, 1.0])      # lin-lin, 2 points
+    # the angular table is read on the energy grid of the law-9 block (scattdata_header.F90:342-368), so it has its rows
+    ad = ace.DistAngle(energy=e9.copy(), type=np.array([ace.ANGLE_TABULAR] * 3, np.int32),
+                       location=np.array([1, 9, 17], np.int32), data=np.concatenate([[0.0], blk, blk, blk]))
+    pv = ace.Tab1(x=np.array([e0, 20.0]), y=np.array([1.0, 1.0]))
+    r9 = ace.Reaction(MT=16, Q_value=-0.9, threshold=thr, scatter_in_cm=False, multiplicity=1,
+                      sigma=np.ones(len(energy) - thr + 1), adist=ad, edist=ace.DistEnergy(law=9, data=d9, p_valid=pv))
+    nuc = ace.Nuclide(awr=26.7, kT=0.0, energy=energy, elastic=np.full(len(energy), 2.0),
+                      reactions=[ace.Reaction(MT=2, threshold=1), r9])
+    e_bins = synth.group_structure(20, 1e-4, 20.0)
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=4, mu_bins=401))
+    rn.convert_distro()
+    m = rn.inelastic(np.array([Ein]))[0][0]
+    T = float(np.interp(Ein, e9, T9))
+    top = Ein - U
+    norm = integrate.quad(lambda e: e * np.exp(-e / T), 0.0, top, epsabs=0, epsrel=1e-13)[0]
+    p = np.array([integrate.quad(lambda e: e * np.exp(-e / T), min(lo, top), min(hi, top), epsabs=0, epsrel=1e-13)[0]
+                  for lo, hi in zip(e_bins[:-1], e_bins[1:])]) / norm
+    assert np.allclose(m[:, 0], p, rtol=1e-9, atol=1e-13)
+    nz = p > 1e-12
+    assert np.allclose(m[nz, 1] / m[nz, 0], b / 3.0, rtol=1e-8)
+    assert np.all(np.abs(m[nz, 2:] / m[nz, :1]) < 1e-8)
+
+
+def test_file6_lab_leg_bin_counting_follows_the_reference_text(oracle):
+    """integrate_file6_lab_leg (src/scattdata_header.F90:1334-1450) is parity unpinned beyond its single-E_out branch.
+    Hand evaluation of the Fortran text on a uniform pdf (41 E_out points on [0, 2], every pdf(i)*dE(i) = 0.025) and the
+    group edges (0, 0.2, 0.5, 0.9, 1.4, 5):  a lower edge adds f_lo * bin (the part *below* the edge, :1385-1391) and then
+    starts at the next bin, an upper edge adds f_hi * bin; edges that coincide with an E_out point have f = 0, and
+    linspace puts E_out(29) just above 1.4 (f = 1 on bin 28 for both neighbours).  Bins counted per group: 3, 5, 7, 9, 13;
+    the final normalisation (:1447-1448) divides by their sum, 37.  The angular part is the table's: P1/P0 = b/3."""
+    from tests.util import heavy_limit_law61
+    nuc, e_bins, params, _ = heavy_limit_law61(awr=55.0, uniform=True)
+    nuc.reactions[1].scatter_in_cm = False
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    m = rn.inelastic(np.array([3.0]))[0][0]
+    assert np.linspace(0.0, 2.0, 41)[28] > 1.4
+    assert np.allclose(m[:, 0], np.array([3.0, 5.0, 7.0, 9.0, 13.0]) / 37.0, rtol=0, atol=1e-12)
+    assert np.allclose(m[:, 1] / m[:, 0], 0.2, rtol=1e-9) and np.all(np.abs(m[:, 2:]) < 1e-9)

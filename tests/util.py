@@ -39,7 +39,7 @@ def small_heavy(n_grid=400, n_levels=6, seed=7, **kw):
                                n_lvl_adist=6, np_lvl=9, **kw)
 
 
-def heavy_limit_law61(b=0.6, awr=1.0e8, NP=41):
+def heavy_limit_law61(b=0.6, awr=1.0e8, NP=41, uniform=False):
     """Analytic pin of unit-base interpolation + integrate_file6_cm_leg (src/scattdata_header.F90:1521-1717, 1085-1266),
     for which the reference holds no test: one CM continuum reaction (Law 61) on an infinitely heavy target, so that
     CM = lab (c -> 0, J -> 1), whose tables are separable -- pdf(E_out) = 2 E / Emax^2 on [0, Emax] (Emax = 0.8 at
@@ -55,7 +55,8 @@ def heavy_limit_law61(b=0.6, awr=1.0e8, NP=41):
         ang = [np.array([2.0, 2.0, -1.0, 1.0, 0.5 * (1 - b), 0.5 * (1 + b), 0.0, 1.0]) for _ in range(NP)]
         LC = pos + 2 + 4 * NP + 8.0 * np.arange(NP)
         locs.append(pos)
-        blocks.append(np.concatenate([[2.0, float(NP)], Eout, 2.0 * Eout / Em ** 2, Eout ** 2 / Em ** 2, LC] + ang))
+        pdf, cdf = (np.full(NP, 1.0 / Em), Eout / Em) if uniform else (2.0 * Eout / Em ** 2, Eout ** 2 / Em ** 2)
+        blocks.append(np.concatenate([[2.0, float(NP)], Eout, pdf, cdf, LC] + ang))
         pos += 2 + 4 * NP + 8 * NP
     data = np.concatenate([[0.0, float(len(e_in))], e_in, np.asarray(locs, float)] + blocks)
     energy = np.geomspace(1e-3, 20.0, 60)
