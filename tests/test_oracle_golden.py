@@ -448,3 +448,127 @@ def test_file6_lab_leg_bin_counting_follows_the_reference_text(oracle):
     assert np.linspace(0.0, 2.0, 41)[28] > 1.4
     assert np.allclose(m[:, 0], np.array([3.0, 5.0, 7.0, 9.0, 13.0]) / 37.0, rtol=0, atol=1e-12)
     assert np.allclose(m[:, 1] / m[:, 0], 0.2, rtol=1e-9) and np.all(np.abs(m[:, 2:]) < 1e-9)
+
+
+@pytest.mark.parametrize("mode", ["equal", "skewed"])
+def test_sab_discrete_inelastic_against_a_numpy_evaluation(oracle, mode):
+    """integrate_sab_inel_disc + combine_sab_grid (src/sab.F90:142-245, 415-454) have no reference test (parity
+    unpinned).  Without an elastic part the combined matrix is sum_{E_out in g} w_j sum_k P_l(mu_jk) over the
+    interpolated table row, divided by its P0 total; evaluated here with numpy's Legendre polynomials, not the
+    reference's explicit ones."""
+    from numpy.polynomial import legendre as npleg
+    sab = synth.c4_sab(mode=mode, elastic=None, n_ein=20, n_eout=16, n_mu=8)
+    e_bins = synth.group_structure(30, 1e-10, 1e-5)
+    rng = np.random.default_rng(8)
+    ein = np.asarray(sab.inelastic_e_in)
+    E = np.sort(np.concatenate([ein[[3, 11]], np.exp(rng.uniform(np.log(ein[0]), np.log(ein[-1]), 12))]))
+    got = oracle.sab_calc(sab, e_bins, 5, E)
+    eo, mu = np.asarray(sab.inelastic_e_out), np.asarray(sab.inelastic_mu)    # [iEin][iEout], [iEin][iEout][imu]
+    n_out, n_mu = eo.shape[1], mu.shape[2]
+    w = np.ones(n_out)
+    if mode == "skewed":
+        w[[0, -1]], w[[1, -2]] = 0.1, 0.4
+    w = w / (w.sum() * n_mu)
+    assert np.array_equal(got[-1], got[-2])          # the last column copies its predecessor (src/sab.F90:452)
+    for i, e in enumerate(E[:-1]):
+        k = min(int(np.searchsorted(ein, e, side="right")) - 1, len(ein) - 2)
+        f = (e - ein[k]) / (ein[k + 1] - ein[k])
+        eo_i = (1 - f) * eo[k] + f * eo[k + 1]
+        mu_i = (1 - f) * mu[k] + f * mu[k + 1]
+        ref = np.zeros((len(e_bins) - 1, 6))
+        for j in range(n_out):
+            if e_bins[0] <= eo_i[j] < e_bins[-1]:
+                g = int(np.searchsorted(e_bins, eo_i[j], side="right")) - 1
+                for l in range(6):
+                    ref[g, l] += w[j] * npleg.legval(mu_i[j], [0] * l + [1]).sum()
+        ref /= ref[:, 0].sum()
+        assert np.allclose(got[i], ref, rtol=1e-11, atol=1e-13), (mode, i)
+
+
+@pytest.mark.parametrize("elastic", ["coherent", "incoherent"])
+def test_sab_elastic_and_combination_against_a_numpy_evaluation(oracle, elastic):
+    """integrate_sab_el (src/sab.F90:21-109: coherent = one cosine 1 - E_bragg/E weighted P/E, incoherent = equally
+    likely interpolated cosines weighted by the interpolated P) and combine_sab_grid ((el + inel) / sum_g P0, :415-454),
+    evaluated independently with numpy."""
+    from numpy.polynomial import legendre as npleg
+    sab = synth.c4_sab(mode="equal", elastic=elastic, n_ein=20, n_eout=16, n_mu=8)
+    e_bins = synth.group_structure(30, 1e-10, 1e-5)
+    rng = np.random.default_rng(9)
+    ee, P = np.asarray(sab.elastic_e_in), np.asarray(sab.elastic_P)
+    E = np.sort(np.exp(rng.uniform(np.log(ee[0] * 1.01), np.log(ee[-1] * 0.99), 15)))
+    out, el, inel = oracle.sab_calc(sab, e_bins, 5, E, parts=True)
+    for i, e in enumerate(E[:-1]):
+        k = int(np.searchsorted(ee, e, side="right")) - 1
+        f = (e - ee[k]) / (ee[k + 1] - ee[k])
+        g = int(np.searchsorted(e_bins, e, side="right")) - 1
+        ref = np.zeros((len(e_bins) - 1, 6))
+        if elastic == "coherent":
+            mu = np.array([1.0 - ee[k] / e])
+            sig, w = P[k] / e, 1.0
+        else:
+            em = np.asarray(sab.elastic_mu)
+            mu = (1 - f) * em[k] + f * em[k + 1]
+            sig, w = (1 - f) * P[k] + f * P[k + 1], 1.0 / em.shape[1]
+        for l in range(6):
+            ref[g, l] = sig * w * npleg.legval(mu, [0] * l + [1]).sum()
+        assert np.allclose(el[i], ref, rtol=1e-11, atol=1e-13 * sig), (elastic, i)
+        tot = el[i] + inel[i]
+        assert np.allclose(out[i], tot / tot[:, 0].sum(), rtol=1e-12, atol=1e-15)
+
+
+def test_sab_continuous_inelastic_against_a_numpy_evaluation(oracle):
+    """integrate_sab_inel_cont (src/sab.F90:253-408, parity unpinned): stage 1 integrates every table row over the
+    groups with the weights pdf(i) * dE(i) and the edge rule of the text (f * bin at both edges, cosines interpolated to
+    the edge), stage 2 interpolates linearly to E_in and scales with the interpolated sigma.  Evaluated with numpy."""
+    from numpy.polynomial import legendre as npleg
+    sab = synth.c4_sab(mode="cont", elastic=None, n_ein=10, n_eout=70, n_mu=6)
+    e_bins = synth.group_structure(24, 1e-10, 1e-5)
+    G, L = len(e_bins) - 1, 6
+    ein, sg = np.asarray(sab.inelastic_e_in), np.asarray(sab.inelastic_sigma)
+
+    def pl(mu):                      # sum over the cosines of P_0..P_5
+        return np.array([npleg.legval(mu, [0] * l + [1]).sum() for l in range(L)])
+
+    def bsearch(a, v):               # 0-based lower index, v == last -> n-2 (src/search.F90)
+        return min(int(np.searchsorted(a, v, side="right")) - 1, len(a) - 2)
+
+    rows = []
+    for d in sab.inelastic_data:
+        Eo, mu = np.asarray(d.e_out), np.asarray(d.mu)        # mu[iEout][imu]
+        w = np.append(np.asarray(d.e_out_pdf)[:-1] * np.diff(Eo), 0.0)
+        dist = np.zeros((G, L))
+        for g in range(G):
+            lo_e, hi_e = e_bins[g], e_bins[g + 1]
+            acc = np.zeros(L)
+            if lo_e < Eo[0]:
+                i_lo = 0
+            elif lo_e >= Eo[-1]:
+                continue
+            else:
+                i = bsearch(Eo, lo_e)
+                f = (lo_e - Eo[i]) / (Eo[i + 1] - Eo[i])
+                acc += f * w[i] * pl((1 - f) * mu[i] + f * mu[i + 1])
+                i_lo = i + 1
+            if hi_e < Eo[0]:
+                continue
+            elif hi_e >= Eo[-1]:
+                i_hi = len(Eo) - 2
+            else:
+                i = bsearch(Eo, hi_e)
+                f = (hi_e - Eo[i]) / (Eo[i + 1] - Eo[i])
+                acc += f * w[i] * pl((1 - f) * mu[i] + f * mu[i + 1])
+                i_hi = i - 1
+            for i in range(i_lo, i_hi + 1):
+                acc += w[i] * pl(mu[i])
+            dist[g] = acc / mu.shape[1]
+        rows.append(dist)
+    rows = np.array(rows)
+    rng = np.random.default_rng(10)
+    E = np.sort(np.concatenate([ein[[2]], np.exp(rng.uniform(np.log(ein[0]), np.log(ein[-1] * 0.999), 10))]))
+    out, el, inel = oracle.sab_calc(sab, e_bins, 5, E, parts=True)
+    for i, e in enumerate(E[:-1]):
+        k = bsearch(ein, e)
+        f = (e - ein[k]) / (ein[k + 1] - ein[k])
+        ref = ((1 - f) * rows[k] + f * rows[k + 1]) * ((1 - f) * sg[k] + f * sg[k + 1])
+        assert np.allclose(inel[i], ref, rtol=1e-10, atol=1e-12 * sg[k]), i
+        assert np.allclose(out[i], ref / ref[:, 0].sum(), rtol=1e-10, atol=1e-13)
