@@ -572,3 +572,61 @@ def test_sab_continuous_inelastic_against_a_numpy_evaluation(oracle):
         ref = ((1 - f) * rows[k] + f * rows[k + 1]) * ((1 - f) * sg[k] + f * sg[k + 1])
         assert np.allclose(inel[i], ref, rtol=1e-10, atol=1e-12 * sg[k]), i
         assert np.allclose(out[i], ref / ref[:, 0].sum(), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("A", [3.5, 15.858])
+@pytest.mark.parametrize("x", [0.4, 3.0, 30.0])
+def test_freegas_p0_matches_the_analytic_kernel_for_any_mass(oracle, A, x):
+    """As test_freegas_p0_matches_the_analytic_kernel_for_A1, for heavier targets (closed form with
+    eta = (A+1)/(2 sqrt A), rho = (A-1)/(2 sqrt A); tests/util.py: freegas_analytic_p0).  Measured agreement 1e-8 .. 9e-7."""
+    from tests.util import freegas_analytic_p0
+    kT = synth.KT_600K
+    energy = np.geomspace(1e-11, 20.0, 200)
+    nuc = ace.Nuclide(awr=A, kT=kT, energy=energy, elastic=np.full(200, 3.8),
+                      reactions=[ace.Reaction(MT=2, threshold=1)], freegas_cutoff=400 * kT)
+    e_bins = synth.group_structure(70)
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=3, mu_bins=2001))
+    rn.convert_distro()
+    m = rn.elastic(np.array([x * kT]))[0]
+    p = freegas_analytic_p0(x * kT, kT, e_bins, A)
+    assert abs(p.sum() - 1.0) < 5e-6
+    assert np.abs(m[:, 0] - p).max() < 5e-6
+
+
+@pytest.mark.parametrize("A,x", [(1.0, 2.0), (15.858, 1.5)])
+def test_freegas_angular_moments_match_a_double_integral_of_the_kernel(oracle, A, x):
+    """P1 .. P3 of the free-gas integrator against scipy's double quadrature of the free-gas law itself,
+    sqrt(E'/E) exp(-(alpha + beta)^2 / 4 alpha) / sqrt(4 pi alpha) P_l(mu) with alpha = (E' + E - 2 mu sqrt(E E'))/(A kT),
+    beta = (E' - E)/kT (constant cross section, isotropic in CM), over the groups next to the one that holds E (the ridge
+    at E' = E, mu = 1 defeats dblquad).  Measured agreement 1e-10 .. 1e-7."""
+    import warnings
+    from numpy.polynomial import legendre as npleg
+    from scipy import integrate
+    kT = synth.KT_600K
+    energy = np.geomspace(1e-11, 20.0, 200)
+    nuc = ace.Nuclide(awr=A, kT=kT, energy=energy, elastic=np.full(200, 3.8),
+                      reactions=[ace.Reaction(MT=2, threshold=1)], freegas_cutoff=400 * kT)
+    e_bins = synth.group_structure(70)
+    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=3, mu_bins=2001))
+    rn.convert_distro()
+    m = rn.elastic(np.array([x * kT]))[0]
+
+    def dd(mu, xp, l):
+        alpha = (xp + x - 2.0 * mu * np.sqrt(x * xp)) / A
+        if alpha <= 0.0:
+            return 0.0
+        return (np.sqrt(xp / x) * np.exp(-(alpha + xp - x) ** 2 / (4.0 * alpha)) / np.sqrt(4.0 * np.pi * alpha) *
+                npleg.legval(mu, [0] * l + [1]))
+    g_in = int(np.searchsorted(e_bins, x * kT, side="right")) - 1
+    groups = [g for g in (g_in - 2, g_in - 1, g_in + 1) if m[g, 0] > 1e-3]
+    assert len(groups) >= 2
+    scale = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for g in groups:
+            lo, hi = e_bins[g] / kT, e_bins[g + 1] / kT
+            v = [integrate.dblquad(dd, lo, hi, -1.0, 1.0, args=(l,), epsabs=1e-11, epsrel=1e-10)[0] for l in range(4)]
+            for l in (1, 2, 3):
+                assert abs(v[l] / v[0] - m[g, l] / m[g, 0]) < 2e-6, (g, l)
+            scale.append(v[0] / m[g, 0])
+    assert np.allclose(scale, scale[0], rtol=5e-6)       # one normalisation constant (sigma_s(E)) for all groups

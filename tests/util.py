@@ -104,3 +104,31 @@ def freegas_a1_analytic_p0(E, kT, e_bins):
         p[g] = integrate.quad(kern, lo, hi, points=[x] if lo < x < hi else None, epsabs=1e-14, epsrel=1e-12,
                               limit=400)[0] / (x * sig)
     return p
+
+
+def freegas_analytic_p0(E, kT, e_bins, A):
+    """Group probabilities of the free-gas kernel for a target of mass ratio A (constant cross section, isotropic in
+    CM; Bell & Glasstone section 7.3): with eta = (A+1)/(2 sqrt A), rho = (A-1)/(2 sqrt A), x = E/kT, x' = E'/kT,
+      sigma(E -> E') ~ eta^2/(2x) { erf(eta sqrt x' - rho sqrt x) +- erf(eta sqrt x' + rho sqrt x)
+                                    + exp(x - x') [erf(eta sqrt x - rho sqrt x') -+ erf(eta sqrt x + rho sqrt x')] }
+    (upper signs for E' < E), normalised by sigma_s(E) ~ [(b^2 + 1/2) erf b + b exp(-b^2)/sqrt pi] / b^2, b^2 = A x."""
+    import warnings
+    from scipy import integrate, special
+    eta, rho = (A + 1.0) / (2.0 * np.sqrt(A)), (A - 1.0) / (2.0 * np.sqrt(A))
+    x = E / kT
+
+    def kern(xp):
+        a, b = np.sqrt(xp), np.sqrt(x)
+        s = 1.0 if xp < x else -1.0
+        return 0.5 * eta * eta / x * (special.erf(eta * a - rho * b) + s * special.erf(eta * a + rho * b) +
+                                      np.exp(x - xp) * (special.erf(eta * b - rho * a) - s * special.erf(eta * b + rho * a)))
+    b2 = A * x
+    tot = ((b2 + 0.5) * special.erf(np.sqrt(b2)) + np.sqrt(b2 / np.pi) * np.exp(-b2)) / b2
+    p = np.zeros(len(e_bins) - 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # the erf differences cancel far from E; quad says so
+        for g in range(len(p)):
+            lo, hi = e_bins[g] / kT, e_bins[g + 1] / kT
+            p[g] = integrate.quad(kern, lo, hi, points=[x] if lo < x < hi else None, epsabs=1e-14, epsrel=1e-12,
+                                  limit=400)[0] / tot
+    return p
