@@ -9,8 +9,12 @@
  * container, so the oracle cannot be checked against the reference binary.  It is pinned by
  * the reference's own known-answer tests (tests/test_scatt/test_scattdata.F90 and the Sage
  * worksheets beside it) -- see tests/test_oracle_golden.py.  Routines for which the reference
- * holds no test (free gas, S(a,b), unit-base, file6_cm_leg, law 9) are "parity unpinned" and
- * are pinned here only by analytic limits.
+ * holds no test (free gas, S(a,b), unit-base, file6_cm_leg, file6_lab_leg, law 9) are "parity
+ * unpinned"; they are held by independent evaluations instead (tests/test_oracle_golden.py): the
+ * closed-form free-gas kernel for A = 1 and general A and a double quadrature of the free-gas law for
+ * P1..P3, numpy evaluations of every S(a,b) routine, the heavy-target limit of unit-base +
+ * file6_cm_leg on separable tables, numerical quadrature of the law-9 spectrum, and a hand evaluation
+ * of the Fortran text of file6_lab_leg.
  *
  * Index convention: all table indices handed around inside the oracle are 1-based, exactly as
  * in the Fortran text; arrays are read through the A1() accessor.
