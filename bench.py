@@ -337,11 +337,13 @@ def run_b200(args):
     f6_ms = st["file6_cm_ms"] / max(1, st["file6_cm_launches"])
     peak = ctx.measure_fp64_peak(0.5)
     achieved = flops / (f6_ms * 1e-3) / 1e12 if f6_ms > 0 else 0.0
-    traffic = None
+    traffic, ncu_extra = None, None
     try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
         if args.n_grid == 20000:
             traffic = tj["traffic_bytes_per_launch"]
+            ncu_extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "achieved_occupancy_pct", "issue_slots_busy_pct",
+                                            "duration_ms_under_ncu", "fp64_issue_floor_ms", "source") if k in tj}
     except Exception:
         pass
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -351,6 +353,8 @@ def run_b200(args):
             "algorithmic_flops_per_launch": flops, "active_E_in": n_act,
             "peak_source": "measured in this run: ndppgpu_measure_fp64_peak (DFMA chains, all SMs); "
                            "MEASURED_PEAKS.json has no FP64 figure"}
+    if ncu_extra:
+        roof["ncu"] = ncu_extra    # counters of the committed ncu --set full capture of this kernel on this workload
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         out_bytes = 8.0 * ev_step
