@@ -630,3 +630,55 @@ def test_freegas_angular_moments_match_a_double_integral_of_the_kernel(oracle, A
                 assert abs(v[l] / v[0] - m[g, l] / m[g, 0]) < 2e-6, (g, l)
             scale.append(v[0] / m[g, 0])
     assert np.allclose(scale, scale[0], rtol=5e-6)       # one normalisation constant (sigma_s(E)) for all groups
+
+
+def test_thin_grid_kept_points_equal_a_numpy_walk_of_the_text(oracle):
+    """thin_grid_one (src/thin.F90:51-169, no reference test) walked literally in numpy: point k is tested against
+    (last kept, k + 1) with log-x interpolation, the error is divided by y *with its sign* (:125-127: a negative y makes
+    any error acceptable), points in `tokeep` stay.  The kept set and the compression must be identical."""
+    rng = np.random.default_rng(21)
+    x = np.geomspace(1e-6, 20.0, 400)
+    y = (np.sin(2.0 * np.log(x))[:, None] + 0.3) * np.linspace(1.0, 2.0, 10)[None, :]      # changes sign
+    y += 1e-4 * rng.normal(size=y.shape)
+    y[50:60] = 0.0                                                                         # y == 0: absolute error
+    tokeep = np.array([x[123], 7.0])
+    tol = 5e-3
+    keep, comp, _, _ = oracle.thin_grid(x, y, tokeep, tol)
+    ref = [0]
+    klo, k = 0, 1
+    while k + 1 < len(x):
+        frac = 1.0 / np.log(x[k + 1] / x[klo]) * np.log(x[k] / x[klo])
+        removable = not np.any(tokeep == x[k])
+        if removable:
+            t = y[klo] + (y[k + 1] - y[klo]) * frac
+            err = np.abs(t - y[k])
+            nz = y[k] != 0.0
+            err[nz] = err[nz] / y[k][nz]
+            removable = bool(np.all(err <= tol))
+        if not removable:
+            ref.append(k)
+            klo = k
+        k += 1
+    ref.append(len(x) - 1)
+    assert np.array_equal(keep, ref)
+    assert comp == (len(x) - len(ref)) / len(x) and 0.2 < comp < 1.0
+
+
+def test_apply_tol_scatt_equals_a_numpy_evaluation_of_the_text(oracle):
+    """apply_tol_scatt (src/scatt.F90:786-818) evaluated in numpy: groups with 0 < P0 < tol are zeroed for every order,
+    then the column is scaled by orig_total / new_total (0 when orig_total <= 0)."""
+    rng = np.random.default_rng(22)
+    d = rng.normal(size=(60, 11, 5)) * 0.2
+    d[:, :, 0] = np.abs(d[:, :, 0]) * (rng.uniform(size=(60, 11)) > 0.2)
+    d[::4, 3, 0] = 4e-9
+    d[7] = 0.0
+    d[9, :, 0] = 0.0                      # orig_total = 0 with non-zero higher moments: norm = 0 wipes the column
+    tol = 1e-8
+    ref = d.copy()
+    for i in range(len(ref)):
+        orig = ref[i, :, 0].sum()
+        small = (ref[i, :, 0] > 0.0) & (ref[i, :, 0] < tol)
+        ref[i, small, :] = 0.0
+        ref[i] *= (orig / ref[i, :, 0].sum()) if orig > 0.0 else 0.0
+    got = oracle.apply_tol_scatt(d, tol)
+    assert np.allclose(got, ref, rtol=1e-15, atol=0.0) and np.all(got[9] == 0.0)
