@@ -682,3 +682,85 @@ def test_apply_tol_scatt_equals_a_numpy_evaluation_of_the_text(oracle):
         ref[i] *= (orig / ref[i, :, 0].sum()) if orig > 0.0 else 0.0
     got = oracle.apply_tol_scatt(d, tol)
     assert np.allclose(got, ref, rtol=1e-15, atol=0.0) and np.all(got[9] == 0.0)
+
+
+def _walk_file4_cm_leg(fw, Ein, awr, Q, E_bins, w, L):
+    """integrate_file4_cm_leg + tolab (src/scattdata_header.F90:956-1078, 1466-1496) walked literally with numpy's
+    Legendre polynomials; 0-based arrays, the 1-based indices of the text kept in ilo / ihi."""
+    from numpy.polynomial import legendre as npleg
+    M = len(w)
+
+    def tolab(R, x):
+        if R > 1.0 or (R == 1.0 and x != -1.0) or (R < 1.0 and not x < -R):
+            return (1.0 + R * x) / np.sqrt(1.0 + R * R + 2.0 * R * x)
+        if R == 1.0:
+            return -1.0
+        f = (x + 1.0) / (-R - 1.0)
+        return (1.0 - f) * (-1.0) + f * np.sqrt(1.0 - R * R)
+
+    def P(u):
+        return np.array([npleg.legval(u, [0] * l + [1]) for l in range(L)])
+    dw = w[1] - w[0]
+    R = awr * np.sqrt(1.0 + Q * (awr + 1.0) / (awr * Ein))
+    out = np.zeros((len(E_bins) - 1, L))
+    for g in range(len(E_bins) - 1):
+        wlo = float(np.clip((E_bins[g] * (1.0 + awr) ** 2 - Ein * (1.0 + R * R)) * 0.5 / (R * Ein), -1.0, 1.0))
+        whi = float(np.clip((E_bins[g + 1] * (1.0 + awr) ** 2 - Ein * (1.0 + R * R)) * 0.5 / (R * Ein), -1.0, 1.0))
+        ilo, ihi = int((wlo + 1.0) / dw) + 1, int((whi + 1.0) / dw) + 1
+        if wlo == whi:
+            if wlo == -1.0:
+                continue
+            if wlo == 1.0:
+                break
+
+        def at(x, i):
+            if i == M:
+                return fw[M - 1]
+            t = (x - w[i - 1]) / (w[i] - w[i - 1])
+            return (1.0 - t) * fw[i - 1] + t * fw[i]
+        flo, fhi = at(wlo, ilo), at(whi, ihi)
+        if ilo != ihi:
+            acc = (w[ilo] - wlo) * (flo * P(tolab(R, wlo)) + fw[ilo] * P(tolab(R, w[ilo])))
+            for iw in range(ilo + 1, ihi):
+                acc = acc + (w[iw] - w[iw - 1]) * (fw[iw - 1] * P(tolab(R, w[iw - 1])) + fw[iw] * P(tolab(R, w[iw])))
+            acc = acc + (whi - w[ihi - 1]) * (fw[ihi - 1] * P(tolab(R, w[ihi - 1])) + fhi * P(tolab(R, whi)))
+        else:
+            acc = (whi - wlo) * (flo * P(tolab(R, wlo)) + fhi * P(tolab(R, whi)))
+        out[g] = 0.5 * acc
+    return out
+
+
+@pytest.mark.parametrize("awr", [236.0058, 11.9])
+def test_file4_cm_leg_and_the_ein_blend_equal_a_numpy_walk_of_the_text(oracle, awr):
+    """Elastic and level-inelastic moments (integrate_distro's lin-lin blend of two integrate_file4_cm_leg calls,
+    src/scattdata_header.F90:530-589) from a literal numpy walk over the oracle's converted tables; level slots are
+    compared up to their sigma * p_valid factor.  Includes energies just above a level threshold, where R < 1."""
+    from tests.util import small_heavy
+    nuc = small_heavy(awr=awr, first_level=0.0449 if awr > 100 else 0.5, level_step=0.05, with_continuum=False)
+    e_bins = synth.group_structure(30, 1e-6, 20.0)
+    params = ace.Params(order=5, mu_bins=401)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    w = -1.0 + 2.0 * np.arange(401) / 400.0
+    w[-1] = 1.0
+    checked = 0
+    for s in (0, 1, 3):
+        info = rn.slot_info(s)
+        assert info["is_init"] and not info["has_edist"]
+        rxn = nuc.reactions[s]
+        eg = rn.slot_egrid(s)
+        thr = nuc.energy[rxn.threshold - 1]
+        lo = max(eg[0], thr)
+        for Ein in (lo * 1.0005, lo * 1.02, np.sqrt(lo * eg[-1]), 0.7 * eg[-1]):
+            iE = min(int(np.searchsorted(eg, Ein, side="right")), len(eg) - 1)       # 1-based lower row
+            f = (Ein - eg[iE - 1]) / (eg[iE] - eg[iE - 1])
+            rows = [rn.get_table(s, i)[0][:, 0] for i in (iE, iE + 1)]
+            ref = (_walk_file4_cm_leg(rows[0], Ein, nuc.awr, rxn.Q_value, e_bins, w, 6) * (1.0 - f) +
+                   _walk_file4_cm_leg(rows[1], Ein, nuc.awr, rxn.Q_value, e_bins, w, 6) * f)
+            got = rn.interp_distro(s, Ein)
+            if rxn.MT != 2:
+                assert got[:, 0].sum() > 0.0
+                got, ref = got / got[:, 0].sum(), ref / ref[:, 0].sum()
+            assert np.allclose(got, ref, rtol=1e-10, atol=1e-13), (s, Ein)
+            checked += 1
+    assert checked == 12
