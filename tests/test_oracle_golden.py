@@ -764,3 +764,166 @@ def test_file4_cm_leg_and_the_ein_blend_equal_a_numpy_walk_of_the_text(oracle, a
             assert np.allclose(got, ref, rtol=1e-10, atol=1e-13), (s, Ein)
             checked += 1
     assert checked == 12
+
+
+def _walk_merge(a, b):
+    """merge (src/array_merge.F90:13-107) walked literally, including the element dropped by its early exit."""
+    d1, d2 = (b, a) if a[-1] > b[-1] else (a, b)
+    n1, n2 = len(d1), len(d2)
+    out, i1, i2, exited = [], 0, 0, False
+    for _ in range(n1 + n2):
+        if i1 < n1 and i2 < n2:
+            if d1[i1] < d2[i2]:
+                out.append(1e-14 if d1[i1] == 0.0 else d1[i1]); i1 += 1
+            elif d1[i1] == d2[i2]:
+                out.append(d1[i1]); i1 += 1; i2 += 1
+            else:
+                out.append(1e-14 if d2[i2] == 0.0 else d2[i2]); i2 += 1
+        elif i1 < n1:
+            out.append(d1[i1]); i1 += 1; exited = True
+            break
+        elif i2 < n2:
+            out.append(d2[i2]); i2 += 1
+        else:
+            out.append(None); exited = True
+            break
+    return np.array(out[:-1] if exited else out, dtype=float)
+
+
+def _walk_unitbase(Ein, Ei1, row1, Ei2, row2):
+    """cast_to_unitbase x 2 + interp_unitbase (src/scattdata_header.F90:1554-1717) for lin-lin / histogram rows;
+    row = (fEmu (M, NP), Eout, pdf, INTT).  Row 2 is interpolated with INTT1, as the text does."""
+    def cast(Eo):
+        dE = Eo[-1] - Eo[0]
+        ub = np.append((Eo[:-1] - Eo[0]) * (1.0 / dE), 1.0)
+        return ub[:-1] if ub[-2] == 1.0 else ub
+
+    def bsearch(a, v):              # 0-based lower index, v == last -> n - 2
+        assert a[0] <= v <= a[-1]
+        return min(int(np.searchsorted(a, v, side="right")) - 1, len(a) - 2)
+    (f1, Eo1, p1, I1), (f2, Eo2, p2, _) = row1, row2
+    ub1, ub2 = cast(Eo1), cast(Eo2)
+    ub = _walk_merge(ub1, ub2)
+    f = (Ein - Ei1) / (Ei2 - Ei1)
+    dE1, dE2 = Eo1[-1] - Eo1[0], Eo2[-1] - Eo2[0]
+    Eout, pdf, fEmu = np.zeros(len(ub)), np.zeros(len(ub)), np.zeros((f1.shape[0], len(ub)))
+    for i, u in enumerate(ub):
+        j = bsearch(ub1, u)
+        r = 0.0 if I1 == 1 else (u - ub1[j]) / (ub1[j + 1] - ub1[j])
+        a = (1.0 - r) * p1[j] + r * p1[j + 1]
+        fEmu[:, i] = (1.0 - f) * ((1.0 - r) * f1[:, j] + r * f1[:, j + 1])
+        j = bsearch(ub2, u)
+        r = 0.0 if I1 == 1 else (u - ub2[j]) / (ub2[j + 1] - ub2[j])
+        b = (1.0 - r) * p2[j] + r * p2[j + 1]
+        fEmu[:, i] += f * ((1.0 - r) * f2[:, j] + r * f2[:, j + 1])
+        pdf[i] = (1.0 - f) * a + f * b
+        Eout[i] = (1.0 - f) * (Eo1[0] + dE1 * u) + f * (Eo2[0] + dE2 * u)
+    return Eout, pdf, fEmu
+
+
+def _walk_file6_cm_leg(fEmu, mu, Ein, awr, Eout, pdf_in, E_bins, L, K=20):
+    """integrate_file6_cm_leg (src/scattdata_header.F90:1085-1266), lin-lin E_out, walked with numpy: vectorised over
+    the lab cosines; the segment integrals of (line) x P_l by 8-point Gauss-Legendre quadrature (exact for the degree)
+    instead of the reference's closed forms."""
+    from numpy.polynomial import legendre as npleg
+    M, n = len(mu), len(Eout)
+    pdf = pdf_in.copy()
+    if Eout[-1] == Eout[-2]:
+        pdf[-2] = 0.0
+    dmu_grid = mu[1] - mu[0]
+    ap1inv = 1.0 / (awr + 1.0)
+    Eo_lo = 1e-12
+    Eo_hi = Eout[-1] + (Ein + 2.0 * (awr + 1.0) * np.sqrt(Ein * Eout[-1])) * ap1inv * ap1inv
+    nb = len(E_bins)
+    assert Eo_lo > E_bins[0] or E_bins[0] == 0.0
+    g_lo = 0 if Eo_lo <= E_bins[0] else int(np.searchsorted(E_bins, Eo_lo, side="right")) - 1
+    if Eo_hi <= E_bins[0]:
+        return np.zeros((nb - 1, L))
+    if Eo_hi >= E_bins[-1]:
+        g_hi, top = nb - 2, E_bins[nb - 2]
+    else:
+        g_hi, top = int(np.searchsorted(E_bins, Eo_hi, side="right")) - 1, Eo_hi
+    gx, gw = npleg.leggauss(8)
+    out = np.zeros((nb - 1, L))
+    for g in range(g_lo, g_hi + 1):
+        lo = Eo_lo if g == g_lo else E_bins[g]
+        hi = top if g == g_hi else E_bins[g + 1]
+        dEo = (hi - lo) / (K - 1.0)
+        Eo = lo - dEo
+        for it in range(K):
+            Eo = Eo + dEo
+            c = ap1inv * np.sqrt(Ein / Eo)
+            mlm = (1.0 + c * c - Eout[-1] / Eo) / (2.0 * c)
+            if mlm < -1.0:
+                mlm = -1.0
+            elif abs(mlm - 1.0) < 1e-10:
+                mlm = 1.0
+            elif mlm > 1.0:
+                continue
+            dmu = (1.0 - mlm) / (M - 1.0)
+            x = mlm + dmu * np.arange(M)
+            Ecm = Eo * (1.0 + c * c - 2.0 * c * x)
+            ok = Ecm > 0.0
+            Es = np.where(ok, Ecm, Eout[0])
+            iEo = np.clip(np.searchsorted(Eout, Es, side="right") - 1, 0, n - 2)
+            iEo = np.where(Es <= Eout[0], 0, np.where(Es >= Eout[-1], n - 2, iEo))
+            den = Eout[iEo + 1] - Eout[iEo]
+            same = den == 0.0
+            fEo = np.where(same, 0.0, (Es - Eout[iEo]) / np.where(same, 1.0, den))
+            pEo = np.where(same, pdf[iEo], (1.0 - fEo) * pdf[iEo] + fEo * pdf[iEo + 1])
+            J = np.sqrt(Eo / Es)
+            mu_c = np.where(x == -1.0, -1.0, np.where(x == 1.0, 1.0, (x - c) * J))
+            ok &= ~((np.abs(mu_c) > 1.0) & (x != -1.0) & (x != 1.0))
+            mc = np.clip(mu_c, -1.0, 1.0)
+            edge = np.abs(mc - 1.0) < 1e-10
+            k0 = np.where(edge, M - 2, ((mc + 1.0) / dmu_grid).astype(int))
+            k0 = np.clip(k0, 0, M - 2)
+            ff = np.where(edge, 1.0, (mc - mu[k0]) / (mu[k0 + 1] - mu[k0]))
+            proby = (1.0 - fEo) * ((1.0 - ff) * fEmu[k0, iEo] + ff * fEmu[k0 + 1, iEo])
+            proby = proby + fEo * ((1.0 - ff) * fEmu[k0, iEo + 1] + ff * fEmu[k0 + 1, iEo + 1])
+            fmu = np.where(ok, proby * J * pEo, 0.0)
+            fEl = np.zeros(L)
+            a, b = x[:-1], x[1:]
+            wide = (b - a) >= 1e-14
+            half, mid = 0.5 * (b - a), 0.5 * (a + b)
+            for q, wq in zip(gx, gw):
+                xq = mid + half * q
+                line = fmu[:-1] + (fmu[1:] - fmu[:-1]) * (xq - a) / np.where(wide, b - a, 1.0)
+                for l in range(L):
+                    fEl[l] += np.sum(np.where(wide, wq * half * line * npleg.legval(xq, [0] * l + [1]), 0.0))
+            out[g] += fEl if it in (0, K - 1) else 2.0 * fEl
+        out[g] *= dEo * 0.5
+    tot = out[g_lo:g_hi + 1, 0].sum()
+    return out * (1.0 / tot if tot > 0.0 else 0.0)
+
+
+@pytest.mark.parametrize("awr", [236.0058, 11.9])
+def test_unitbase_and_file6_cm_leg_equal_a_numpy_walk_of_the_text(oracle, awr):
+    """The dominant path (unit-base interpolation + integrate_file6_cm_leg on Law-44 tables) from a numpy walk of the
+    Fortran text over the oracle's converted tables; the segment integrals come from Gauss-Legendre quadrature, so the
+    comparison is limited by the round-off of the reference's closed forms (measured agreement 3e-14 .. 3e-11 of P0)."""
+    from tests.util import small_heavy
+    nuc = small_heavy(awr=awr, first_level=0.0449 if awr > 100 else 0.5, level_step=0.05)
+    e_bins = synth.group_structure(24, 1e-4, 20.0)
+    params = ace.Params(order=4, mu_bins=201)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    s = [k for k in range(rn.n_slots) if rn.slot_info(k)["is_init"] and rn.slot_info(k)["law"] == 44]
+    assert len(s) == 1
+    s = s[0]
+    eg = rn.slot_egrid(s)
+    mu = -1.0 + 2.0 * np.arange(201) / 200.0
+    mu[-1] = 1.0
+    for Ein in (eg[0] * 1.01, 0.5 * (eg[2] + eg[3]), 0.93 * eg[-1]):
+        iE = min(int(np.searchsorted(eg, Ein, side="right")), len(eg) - 1)
+        rows = []
+        for i in (iE, iE + 1):
+            d, Eo, pdf, _, intt = rn.get_table(s, i)
+            rows.append((d, Eo, pdf, intt))
+        Eout, pdf, fEmu = _walk_unitbase(Ein, eg[iE - 1], rows[0], eg[iE], rows[1])
+        ref = _walk_file6_cm_leg(fEmu, mu, Ein, nuc.awr, Eout, pdf, e_bins, 5)
+        got = rn.interp_distro(s, Ein)
+        assert got[:, 0].sum() > 0.0
+        got = got / got[:, 0].sum()
+        assert abs(ref[:, 0].sum() - 1.0) < 1e-12
+        assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref) + 1e-9), (Ein, np.abs(got - ref).max())
