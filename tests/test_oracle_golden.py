@@ -927,3 +927,38 @@ def test_unitbase_and_file6_cm_leg_equal_a_numpy_walk_of_the_text(oracle, awr):
         got = got / got[:, 0].sum()
         assert abs(ref[:, 0].sum() - 1.0) < 1e-12
         assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref) + 1e-9), (Ein, np.abs(got - ref).max())
+
+
+def test_inelastic_grid_is_the_ordered_sum_of_the_slots(oracle):
+    """calc_inelastic_grid (src/scatt.F90:682-778): inel_mat = sum over the non-elastic slots of interp_distro in slot
+    order, nuinel_mat = the same sum weighted with the multiplicities; interp_distro scales a level's distribution by
+    sigma(E_in) (lin-lin on the nuclide grid, scattdata_header.F90:447-497), so its P0 total is sigma to the accuracy of
+    the trapezoid in mu; the elastic matrix is not sigma-weighted and has P0 total 1."""
+    from tests.util import small_heavy
+    nuc = small_heavy()
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=3, mu_bins=2001, nuscatter=True)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    Ein = np.array([0.3, 1.7, 6.5])
+    inel, nu = rn.inelastic(Ein)
+    el = rn.elastic(Ein)
+    assert np.allclose(el[:, :, 0].sum(axis=1), 1.0, atol=2e-6)
+    for i, E in enumerate(Ein):
+        tot, nutot = np.zeros_like(inel[i]), np.zeros_like(inel[i])
+        for s in range(1, rn.n_slots):
+            if not rn.slot_info(s)["is_init"]:
+                continue
+            rxn = nuc.reactions[s]
+            if E < nuc.energy[rxn.threshold - 1]:
+                continue
+            d = rn.interp_distro(s, E)
+            tot = tot + d
+            nutot = nutot + float(rxn.multiplicity) * d
+            if rn.slot_info(s)["law"] in (0, 3):           # a level: P0 total = sigma(E)
+                k = int(np.searchsorted(nuc.energy, E, side="right")) - 1
+                f = (E - nuc.energy[k]) / (nuc.energy[k + 1] - nuc.energy[k])
+                j = k - (rxn.threshold - 1)
+                sig = (1 - f) * rxn.sigma[j] + f * rxn.sigma[j + 1]
+                assert abs(d[:, 0].sum() - sig) <= 1e-4 * sig + 1e-12, (s, E)
+        assert np.array_equal(inel[i], tot) and np.array_equal(nu[i], nutot)
