@@ -3,8 +3,10 @@
  *
  * CPU restatement of the reference's free-gas thermal kernel integrator, src/freegas.F90:18-644.
  * Recursive, exactly as the Fortran text; PI is the reference's truncated constant.
- * Parity status: the reference holds no test for this module => "parity unpinned"; pinned in
- * tests/ by analytic limits only (normalisation, kT->0 limit).
+ * Parity status: the reference holds no test for this module => "parity unpinned"; held in tests/ by
+ * the closed-form free-gas kernel (A = 1 and general A), a double quadrature of the free-gas law for
+ * P1..P3, and a literal pure-Python transcription of the Fortran text (tests/freegas_walk.py) that
+ * this file reproduces bit for bit.
  * Build: gcc -O2 -ffp-contract=off (oracle/Makefile).
  */
 #include <math.h>

@@ -8,8 +8,8 @@
  *   combine_sab_grid         src/sab.F90:415-454
  *   calc_scattsab            src/scatt.F90:543-596  (Legendre branch)
  * Serial semantics (the reference's OpenMP build races on `sig`).
- * Parity status: no reference test exists for this module => "parity unpinned"; tests pin it
- * with analytic properties (sum_g P0 = 1, P1 = mean cosine).
+ * Parity status: no reference test exists for this module => "parity unpinned"; tests hold every
+ * routine against an independent numpy evaluation of the Fortran text (tests/test_oracle_golden.py).
  *
  * Flattening of type(SAlphaBeta) (src/ace_header.F90:201-235), Fortran column-major kept:
  *   inelastic_e_out(NEo,NEi)      -> e_out[(isab-1)*NEo + (iEout-1)]

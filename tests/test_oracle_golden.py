@@ -962,3 +962,48 @@ def test_inelastic_grid_is_the_ordered_sum_of_the_slots(oracle):
                 sig = (1 - f) * rxn.sigma[j] + f * rxn.sigma[j + 1]
                 assert abs(d[:, 0].sum() - sig) <= 1e-4 * sig + 1e-12, (s, E)
         assert np.array_equal(inel[i], tot) and np.array_equal(nu[i], nutot)
+
+
+def test_freegas_restatement_equals_a_literal_python_walk_of_the_text(oracle):
+    """src/freegas.F90 has no reference test.  tests/freegas_walk.py transcribes it from the Fortran text in pure
+    Python; with the adaptive tolerances loosened in both (the algorithm is the same at any tolerance) the restatement
+    must reproduce the walk's value tree: H-1 with an isotropic CM table, and A = 15.858 with a tabular table between two
+    incoming-energy rows (the lin-lin blend of two integrate_freegas_leg calls, scattdata_header.F90:530-589)."""
+    from tests.freegas_walk import make_walk
+    M = 2001
+    gmu = list(-1.0 + np.arange(M) * (2.0 / (M - 1)))
+    gmu[-1] = 1.0
+    tol = dict(adaptive_mu_tol=1e-4, adaptive_mu_its=8, adaptive_eout_tol=1e-5, adaptive_eout_its=8)
+    params = ace.Params(order=2, mu_bins=M, **tol)
+    e_bins = np.array([0.0, 1e-9, 2e-8, 6e-8, 2e-7, 1e-6, 20.0])
+    energy = np.geomspace(1e-11, 20.0, 100)
+    evals = 0
+    # H-1, isotropic
+    kT = synth.KT_293K
+    nuc = ace.Nuclide(awr=0.999167, kT=kT, energy=energy, elastic=np.full(100, 20.0),
+                      reactions=[ace.Reaction(MT=2, threshold=1)], freegas_cutoff=400 * kT)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    walk = make_walk(nuc.awr, kT, list(rn.get_table(0, 1)[0][:, 0]), gmu, 3, 1e-4, 8, 1e-5, 8, params.sab_threshold,
+                     params.brent_mu_thresh)
+    for x in (0.5, 4.0, 40.0):
+        ref, n = walk(x * kT, list(e_bins))
+        evals = n
+        assert np.abs(rn.elastic(np.array([x * kT]))[0] - ref).max() <= 1e-15, x
+    # A = 15.858, forward-peaked tabular rows, E_in between two rows
+    kT = synth.KT_600K
+    ad = synth.make_adist([1e-11, 1e-6, 20.0], [ace.ANGLE_TABULAR] * 3, [0.0, 0.3, 2.0], NP_tab=11)
+    nuc = ace.Nuclide(awr=15.858, kT=kT, energy=energy, elastic=np.full(100, 3.8),
+                      reactions=[ace.Reaction(MT=2, threshold=1, adist=ad)], freegas_cutoff=400 * kT)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    rows = [list(rn.get_table(0, i)[0][:, 0]) for i in (1, 2)]
+    for E in (3e-9, 4.1e-7):
+        f = (E - 1e-11) / (1e-6 - 1e-11)
+        parts = []
+        for r in rows:
+            w = make_walk(nuc.awr, kT, r, gmu, 3, 1e-4, 8, 1e-5, 8, params.sab_threshold, params.brent_mu_thresh)
+            parts.append(w(E, list(e_bins))[0])
+        ref = parts[0] * (1.0 - f) + parts[1] * f
+        assert np.abs(rn.elastic(np.array([E]))[0] - ref).max() <= 1e-15, E
+    assert evals > 100000
