@@ -513,3 +513,29 @@ def test_freegas_p0_matches_the_analytic_kernel_for_A1(scatt):
     for i, x in enumerate(xs):
         p = freegas_a1_analytic_p0(x * nuc.kT, nuc.kT, eb)
         assert np.abs(got[i, :, 0] - p).max() < 5e-6, x
+
+
+def test_cuda_against_the_committed_walk_vectors(scatt):
+    """The CUDA path against tests/golden/walk_vectors.npz: moments computed by literal walks of the Fortran text
+    (scripts/make_walk_golden.py) with neither the oracle's integrators nor CUDA -- free gas at the reference's default
+    adaptive tolerances (same allowance as test_c3_freegas for accept / split decisions taken on exp()), and the Law-44
+    continuum through unit-base interpolation + integrate_file6_cm_leg (device-converted tables: round-off floor)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_walk_golden", os.path.join(root, "scripts", "make_walk_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    v = np.load(os.path.join(root, "tests", "golden", "walk_vectors.npz"))
+    nuc, e_bins, params, Ein = mk.freegas_case()
+    got = scatt.DeviceNuclide(nuc, e_bins, params).elastic(Ein)
+    ref = v["freegas_moments"]
+    err = np.abs(got - ref)
+    ok = (err <= 1e-9 * np.abs(ref)) | (err <= 1e-12)
+    assert np.count_nonzero(~ok) <= 2 and err.max() < 1e-6
+    nuc, e_bins, params = mk.file6_case()
+    dn = scatt.DeviceNuclide(nuc, e_bins, params)
+    for E, ref in zip(v["file6_Ein"], v["file6_moments"]):
+        m = dn.interp_distro(int(v["file6_slot"]), np.array([float(E)]))[0]
+        m = m / m[:, 0].sum()
+        assert np.all(np.abs(m - ref) <= 1e-9 * np.abs(ref) + 1e-8), float(E)

@@ -1007,3 +1007,27 @@ def test_freegas_restatement_equals_a_literal_python_walk_of_the_text(oracle):
         ref = parts[0] * (1.0 - f) + parts[1] * f
         assert np.abs(rn.elastic(np.array([E]))[0] - ref).max() <= 1e-15, E
     assert evals > 100000
+
+
+def test_oracle_reproduces_the_committed_walk_vectors(oracle):
+    """tests/golden/walk_vectors.npz (scripts/make_walk_golden.py): moments from the literal walks of the Fortran text,
+    the free-gas ones at the reference's default adaptive tolerances."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_walk_golden", os.path.join(root, "scripts", "make_walk_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    v = np.load(os.path.join(root, "tests", "golden", "walk_vectors.npz"))
+    nuc, e_bins, params, Ein = mk.freegas_case()
+    assert np.array_equal(v["freegas_Ein"], Ein) and np.array_equal(v["freegas_e_bins"], e_bins)
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    assert np.abs(rn.elastic(Ein) - v["freegas_moments"]).max() <= 1e-15
+    nuc, e_bins, params = mk.file6_case()
+    rn = oracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    for E, ref in zip(v["file6_Ein"], v["file6_moments"]):
+        got = rn.interp_distro(int(v["file6_slot"]), float(E))
+        got = got / got[:, 0].sum()
+        assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref) + 1e-9)
