@@ -214,6 +214,12 @@ int ndppgpu_inelastic_thinned(void *nuc, double *Ein, int NE, double print_tol, 
  * per_thread random operand pairs per GPU thread.  counts2 = {pairs, mismatches}; mismatches must be zero. */
 int ndppgpu_test_exact_math(void *ctx, unsigned long long seed, int per_thread, unsigned long long *counts2);
 
+/* The device's sinh / cosh / expm1 / exp (csrc/libm_exact.cuh: a restatement of the algorithms of the host C library
+ * the reference's Fortran calls, GNU libc 2.39 x86-64 FMA builds) at n host arguments; fn = 0 exp, 1 expm1, 2 sinh,
+ * 3 cosh.  convert_file6's Law 44 (src/scattdata_header.F90:822-831) is built from these, and the parity tests compare
+ * them bit for bit with the running libm. */
+int ndppgpu_eval_libm(void *ctx, int fn, const double *x, long long n, double *y);
+
 int ndppgpu_test_legendre(void *ctx, int n, int L, const double *xlow, const double *xhigh, const double *flow,
                           const double *fhigh, double *integrals, double *pn);
 

@@ -26,7 +26,7 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
            "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
-           "ndppgpu_inelastic_thinned", "ndppgpu_chi"]
+           "ndppgpu_inelastic_thinned", "ndppgpu_chi", "ndppgpu_eval_libm"]
 
 
 class NdppGpuError(RuntimeError):
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     L.ndppgpu_interp_distro.argtypes = [vp, i, c_dp, i, c_dp]
     L.ndppgpu_nuclide_set_table.argtypes = [vp, i, i, c_dp]
     L.ndppgpu_test_legendre.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L.ndppgpu_eval_libm.argtypes = [vp, i, c_dp, C.c_longlong, c_dp]
     L.ndppgpu_test_exact_math.argtypes = [vp, C.c_ulonglong, i, C.POINTER(C.c_ulonglong)]
     L.ndppgpu_apply_tol.argtypes = [vp, c_dp, i, i, i, d]
     L.ndppgpu_apply_tol_dev.argtypes = [vp, vp, i, i, i, d]
@@ -166,6 +167,13 @@ class Context:
         out = (C.c_ulonglong * 2)()
         check(self.lib.ndppgpu_test_exact_math(self.h, int(seed), int(per_thread), out), self.h)
         return {"pairs": out[0], "mismatch": out[1]}
+
+    def eval_libm(self, fn, x):
+        """The device's exp (0) / expm1 (1) / sinh (2) / cosh (3) of csrc/libm_exact.cuh at the host array x."""
+        x = f64(x)
+        y = np.empty_like(x)
+        check(self.lib.ndppgpu_eval_libm(self.h, int(fn), dp(x), len(x), dp(y)), self.h)
+        return y
 
     @property
     def stream(self) -> int:

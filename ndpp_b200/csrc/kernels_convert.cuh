@@ -8,6 +8,7 @@
 // conversion data-parallel without changing any result.
 #pragma once
 #include "common.cuh"
+#include "libm_exact.cuh"
 
 namespace ndpp {
 
@@ -60,7 +61,11 @@ __global__ void k_convert_file4(SlotDev s, const double* __restrict__ mu)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)s.NE * M) return;
     const int iE = (int)(t / M), imu = (int)(t % M);
-    s.tab[(size_t)s.row_off[iE] * M + imu] = convert_file4_point(s, iE, mu[imu], imu);
+    // A law-9 slot takes NE from its energy distribution but indexes the angular distribution with the same
+    // row number (:345-350); past the end of adist the reference reads out of bounds (undefined).  Rows beyond
+    // the last angular entry use that entry (the synthesised adist is isotropic throughout).
+    const int iEad = iE < s.ad_n ? iE : s.ad_n - 1;
+    s.tab[(size_t)s.row_off[iE] * M + imu] = convert_file4_point(s, iEad, mu[imu], imu);
 }
 
 #define EDATA(k) data[(k)-1]
@@ -71,7 +76,9 @@ __device__ __forceinline__ double law61_point(const double* data, int lc, double
     const int interp = (int)EDATA(lc + 1);
     const int NPang = (int)EDATA(lc + 2);
     lc = lc + 3;
-    if (interp < HISTOGRAM || interp > LOG_LOG) return 0.0;  // reference: fatal_error (:944)
+    // an unknown interpolation code is the reference's fatal_error (:944); the host rejects it in
+    // ndppgpu_nuclide_add_reaction before any table is built (validate_law61)
+    if (interp < HISTOGRAM || interp > LOG_LOG) return 0.0;
     for (int idata = lc; idata <= lc + NPang - 1; ++idata) {
         if ((EDATA(idata) - mu) > FP_PRECISION) {
             double r;
@@ -85,10 +92,10 @@ __device__ __forceinline__ double law61_point(const double* data, int lc, double
                 return EDATA(idata + NPang - 1) + r * (EDATA(idata + NPang) - EDATA(idata - 1 + NPang));
             case LOG_LINEAR:
                 r = (mu - EDATA(idata - 1)) / (EDATA(idata) - EDATA(idata - 1));
-                return exp((1.0 - r) * log(EDATA(idata + NPang)) + r * log(EDATA(idata + NPang - 1)));
+                return lm::exp_((1.0 - r) * log(EDATA(idata + NPang)) + r * log(EDATA(idata + NPang - 1)));
             default:  // LOG_LOG
                 r = (log(mu) - log(EDATA(idata - 1))) / (log(EDATA(idata)) - log(EDATA(idata - 1)));
-                return exp((1.0 - r) * log(EDATA(idata + NPang)) + r * log(EDATA(idata + NPang - 1)));
+                return lm::exp_((1.0 - r) * log(EDATA(idata + NPang)) + r * log(EDATA(idata + NPang - 1)));
             }
         }
         if (fabs(EDATA(idata) - mu) <= FP_PRECISION) return EDATA(idata + NPang);
@@ -134,8 +141,9 @@ __global__ void k_convert_file6(SlotDev s, const double* __restrict__ mu, double
         const int lc = lc0 + 2;
         const double KMR = EDATA(lc + 3 * NP + (iEout + 1));
         const double KMA = EDATA(lc + 4 * NP + (iEout + 1));
-        const double KMconst = 0.5 * KMA / sinh(KMA);
-        v = KMconst * (cosh(KMA * x) + KMR * sinh(KMA * x));
+        // sinh / cosh with the bits of the host libm the reference calls (libm_exact.cuh)
+        const double KMconst = 0.5 * KMA / lm::sinh_(KMA);
+        v = KMconst * (lm::cosh_(KMA * x) + KMR * lm::sinh_(KMA * x));
     } else if (s.edist_law == 61) {
         const int lcin = lc0 + 2;
         const int lc = (int)EDATA(lcin + 3 * NP + (iEout + 1));

@@ -126,9 +126,11 @@ __global__ void k_elastic(NucDev nuc, const SlotDev* __restrict__ slots, const i
     if (!(E <= nuc.e_bins[nuc.n_bins - 1])) return;  // k_copy_top
     for (int k = 0; k < n_el; ++k) {
         const SlotDev& s = slots[el_ids[k]];
-        if (E < nuc.freegas_cutoff) continue;        // free-gas column
+        // zero first: a free-gas column whose interpolated elastic xs is <= 0 is written by nobody else
+        // (scatt_interp_distro returns distro = ZERO there, scattdata_header.F90:414-419)
         for (int e = lane; e < GL; e += 32) col[e] = 0.0;
         __syncwarp();
+        if (E < nuc.freegas_cutoff) continue;        // free-gas column: k_freegas_finish overwrites the active ones
         const InterpInfo info = interp_info(nuc, s, E);
         if (info.active) file4_cm_warp(nuc, s, info, E, col);
         __syncwarp();

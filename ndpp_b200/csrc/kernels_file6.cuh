@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(128, NDPP_F6_MINBLOCKS) k_file6_cm(NucDev nuc,
 // Normalisation over the groups (:1255-1264; raw is zero outside g_lo..g_hi, so summing over all
 // groups in order gives the same value) followed by distro * sigS * p_valid (:494-497).
 // One warp per E_in; out may alias raw.
-__global__ void k_file6_finish(NucDev nuc, UbDev ub, int NE, const double* __restrict__ raw, double* __restrict__ out,
-                               int guard)
+// raw and out may alias (the callers finish a slab in place): no __restrict__ on either.
+__global__ void k_file6_finish(NucDev nuc, UbDev ub, int NE, const double* raw, double* out, int guard)
 {
     const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;

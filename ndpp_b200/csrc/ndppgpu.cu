@@ -288,6 +288,29 @@ void scatt_init(Nuclide* n, Slot* s, HostRxn* rxn, int edist_assoc, int edist_la
     s->is_init = 1;
 }
 
+// convert_file6's fatal_error for a Law-61 angular table with an interpolation code outside 1..5
+// (src/scattdata_header.F90:843-945), checked before any table is built.  Returns the offending code or 0.
+int validate_law61(const Slot* s)
+{
+    const double* d = s->edist_data.data();
+    const long long nd = (long long)s->edist_data.size();
+    auto at = [&](long long k) -> double { return (k >= 1 && k <= nd) ? d[k - 1] : 0.0; };  // Fortran data(k)
+    const int NR = (int)at(1);
+    const int NE = (int)at(2 + 2 * NR);
+    for (int i = 1; i <= NE; ++i) {
+        const long long lc0 = (long long)at(2 + 2 * NR + NE + i);
+        const int NP = (int)at(lc0 + 2);
+        const long long lcin = lc0 + 2;
+        for (int j = 1; j <= NP; ++j) {
+            const long long lc = (long long)at(lcin + 3LL * NP + j);
+            if (lc == 0) continue;   // isotropic
+            const int interp = (int)at(lc + 1);
+            if (interp < HISTOGRAM || interp > LOG_LOG) return interp == 0 ? -1 : interp;
+        }
+    }
+    return 0;
+}
+
 // Host staging arena of one nuclide: every small array of every slot is appended (16-byte aligned) and the
 // whole arena crosses PCIe in one copy -- per-array uploads with their stream synchronisations cost ~10 ms per
 // heavy nuclide (42 slots x 10 arrays), which dominated a library run's set-up.
@@ -449,6 +472,15 @@ __global__ void k_test_exact_math(unsigned long long seed, int per_thread, unsig
     }
     atomicAdd(&counts[0], (unsigned long long)per_thread);
     atomicAdd(&counts[1], bad);
+}
+
+// the device build of libm_exact.cuh at given arguments (ndppgpu_eval_libm)
+__global__ void k_eval_libm(int fn, const double* __restrict__ x, double* __restrict__ y, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        y[i] = fn == 2 ? lm::sinh_(v) : fn == 3 ? lm::cosh_(v) : fn == 1 ? lm::expm1_(v) : lm::exp_(v);
+    }
 }
 
 // fatal_error of the reference's binary_search (src/search.F90:36-38), latched by the kernels
@@ -687,10 +719,8 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             // items of bounded size that are processed generation by generation (kernels_freegas.cuh); the item
             // queue and its token arena start from an estimate.  The kernels flag either overflow, in which case
             // the call is repeated with the worst-case scratch / a queue four times as large.
-            cudaDeviceProp prop;
-            CK(c, cudaGetDeviceProperties(&prop, c->device));
             const long long n_root = tasks * rows;
-            const int max_blocks = (int)std::min<long long>((long long)prop.multiProcessorCount * FG_BLOCKS_PER_SM,
+            const int max_blocks = (int)std::min<long long>((long long)c->sm_count * FG_BLOCKS_PER_SM,
                                                             (n_root + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
             const size_t warps = (size_t)max_blocks * FG_WARPS_PER_BLOCK, full = (size_t)1 << n->p.adaptive_mu_its;
             TmpBuf d_ovf, d_items, d_ival, d_roff, d_rlen, d_ops, d_pay, d_tails;
@@ -1074,6 +1104,15 @@ int ndppgpu_nuclide_add_reaction(void* nuc, int rxn_index, int MT, double Q_valu
     HostRxn* r = nullptr;
     for (auto& q : n->rxns) if (q->id == rxn_index) r = q.get();
     if (!r) {
+        // validate first: a failing call must not leave a half-built reaction behind for a retry to reuse
+        if (has_angle_dist && (!adist_energy || !adist_type || !adist_loc || n_adist_e < 1))
+            return fail(c, "ndppgpu_nuclide_add_reaction: has_angle_dist set but no angular data");
+        if (is_valid_scatter(MT)) {
+            if (threshold < 1 || threshold > (int)n->energy.size())
+                return fail(c, "ndppgpu_nuclide_add_reaction: threshold index outside the energy grid");
+            if (MT != 2 && n_sigma != (int)n->energy.size() - threshold + 1)
+                return fail(c, "ndppgpu_nuclide_add_reaction: sigma length must be n_grid - threshold + 1");
+        }
         n->rxns.emplace_back(new HostRxn());
         r = n->rxns.back().get();
         r->id = rxn_index; r->MT = MT; r->Q = Q_value; r->multiplicity = multiplicity; r->threshold = threshold;
@@ -1081,18 +1120,10 @@ int ndppgpu_nuclide_add_reaction(void* nuc, int rxn_index, int MT, double Q_valu
         if (yield_tab1 && n_yield > 0) r->yield.assign(yield_tab1, yield_tab1 + n_yield);
         if (sigma && n_sigma > 0) r->sigma.assign(sigma, sigma + n_sigma);
         if (has_angle_dist) {
-            if (!adist_energy || !adist_type || !adist_loc || n_adist_e < 1)
-                return fail(c, "ndppgpu_nuclide_add_reaction: has_angle_dist set but no angular data");
             r->ad_energy.assign(adist_energy, adist_energy + n_adist_e);
             r->ad_type.assign(adist_type, adist_type + n_adist_e);
             r->ad_loc.assign(adist_loc, adist_loc + n_adist_e);
             if (adist_data && n_adist_data > 0) r->ad_data.assign(adist_data, adist_data + n_adist_data);
-        }
-        if (is_valid_scatter(MT)) {
-            if (threshold < 1 || threshold > (int)n->energy.size())
-                return fail(c, "ndppgpu_nuclide_add_reaction: threshold index outside the energy grid");
-            if (MT != 2 && n_sigma != (int)n->energy.size() - threshold + 1)
-                return fail(c, "ndppgpu_nuclide_add_reaction: sigma length must be n_grid - threshold + 1");
         }
     }
     n->slots.emplace_back(new Slot());
@@ -1100,14 +1131,19 @@ int ndppgpu_nuclide_add_reaction(void* nuc, int rxn_index, int MT, double Q_valu
     if (edist_data && n_edist_data > 0) s->edist_data.assign(edist_data, edist_data + n_edist_data);
     if (p_valid_tab1 && n_pvalid > 0) s->p_valid.assign(p_valid_tab1, p_valid_tab1 + n_pvalid);
     s->edist_law = law;
+    auto reject = [&](const std::string& msg) { n->slots.pop_back(); return fail(c, msg); };
     if (has_energy_dist && (law == 4 || law == 44 || law == 61) && is_valid_scatter(r->MT)) {
-        if (s->edist_data.size() < 2) return fail(c, "ndppgpu_nuclide_add_reaction: energy distribution data missing");
+        if (s->edist_data.size() < 2) return reject("ndppgpu_nuclide_add_reaction: energy distribution data missing");
         if ((int)s->edist_data[0] > 0)  // convert_file6 :797-800
-            return fail(c, "Multiple interpolation regions not supported while attempting to sample Kalbach-Mann distribution.");
+            return reject("Multiple interpolation regions not supported while attempting to sample Kalbach-Mann distribution.");
     }
     scatt_init(n, s, r, has_energy_dist, law);
     if (s->is_init && s->has_edist && s->p_valid.empty())
-        return fail(c, "ndppgpu_nuclide_add_reaction: energy distribution without p_valid");
+        return reject("ndppgpu_nuclide_add_reaction: energy distribution without p_valid");
+    if (s->is_init && s->has_edist && s->law == 61) {
+        const int bad = validate_law61(s);
+        if (bad != 0) return reject("Unknown interpolation type: " + std::to_string(bad == -1 ? 0 : bad));  // convert_file6 :944
+    }
     return 0;
 }
 
@@ -1695,14 +1731,28 @@ int ndppgpu_chi(void* ctx, int n_grid, const double* energy, const double* fissi
     }
 }
 
+int ndppgpu_eval_libm(void* ctx, int fn, const double* x, long long n, double* y)
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !x || !y) return fail(c, "ndppgpu_eval_libm: null argument");
+    if (fn < 0 || fn > 3) return fail(c, "ndppgpu_eval_libm: fn must be 0 (exp), 1 (expm1), 2 (sinh) or 3 (cosh)");
+    if (n <= 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    TmpBuf dx, dy;
+    if (tmp_upload(c, dx, x, (size_t)n) || tmp_alloc(c, dy, (size_t)n * sizeof(double))) return 1;
+    k_eval_libm<<<8 * c->sm_count, 256, 0, c->stream>>>(fn, dx.as<double>(), dy.as<double>(), n);
+    if (launch_check(c, "k_eval_libm")) return 1;
+    CK(c, cudaMemcpyAsync(y, dy.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int ndppgpu_measure_fp64_peak(void* ctx, double seconds, double* tflops)
 {
     Ctx* c = (Ctx*)ctx;
     if (!c || !tflops) return fail(c, "ndppgpu_measure_fp64_peak: null argument");
     CK(c, cudaSetDevice(c->device));
-    cudaDeviceProp prop;
-    CK(c, cudaGetDeviceProperties(&prop, c->device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    const int blocks = c->sm_count * 8, threads = 256, iters = 1 << 16;
     DevBuf out;
     if (dev_alloc(c, out, (size_t)blocks * threads * sizeof(double))) return 1;
     cudaEvent_t a, b;

@@ -103,7 +103,8 @@ def _make_items(shapes, G, L, M, K, tile_rows, cont_split) -> List[WorkItem]:
         if s.n_inel <= 0:
             continue
         thr = sorted(s.level_thresholds)
-        e0 = min(list(thr) + ([s.cont_threshold] if s.cont_threshold is not None else []))
+        # a nuclide whose inelastic slots are all (n,2n)-like (no level, no continuum threshold) starts at the grid
+        e0 = min(list(thr) + ([s.cont_threshold] if s.cont_threshold is not None else []), default=s.e_lo)
         inel_lo = dict(e_lo=max(e0, s.e_lo), e_hi=s.e_hi)
         nt = max(1, -(-s.n_inel // tile_rows))
         if s.cont_threshold is not None:

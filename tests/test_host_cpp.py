@@ -11,7 +11,7 @@ import pytest
 
 from ndpp_b200 import ace, dump, synth
 from ndpp_b200 import build as nbuild
-from tests.util import assert_parity, assert_parity_floor, small_heavy
+from tests.util import assert_parity, small_heavy
 
 
 @pytest.fixture(scope="module")
@@ -168,8 +168,8 @@ def test_cpp_calc_scatt_c1(tool, oracle, tmp_path):
     rn.convert_distro()
     assert_parity(el, rn.elastic(Ein), what="C++ calc_scatt C1 elastic")
     ri, rnu = rn.inelastic(Ein_inel)
-    assert_parity_floor(inel, ri, what="C++ calc_scatt C1 inelastic")
-    assert_parity_floor(nu, rnu, what="C++ calc_scatt C1 nu-inelastic")
+    assert_parity(inel, ri, what="C++ calc_scatt C1 inelastic")
+    assert_parity(nu, rnu, what="C++ calc_scatt C1 nu-inelastic")
     # nuscatt = .false. and no inelastic grid: the two matrices stay unallocated (src/scatt.F90:146-150)
     dump.write_nuclide_case(tmp_path / "c1b.case", nuc, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 3001, False, Ein, None, params)
     _run(tool, tmp_path / "c1b.case", tmp_path / "c1b.res")
@@ -193,8 +193,8 @@ def test_cpp_calc_scatt_heavy_shape(tool, oracle, tmp_path):
     rn.convert_distro()
     assert_parity(el, rn.elastic(Ein), what="C++ calc_scatt heavy elastic")
     ri, rnu = rn.inelastic(Ein_inel)
-    assert_parity_floor(inel, ri, what="C++ calc_scatt heavy inelastic")
-    assert_parity_floor(nu, rnu, what="C++ calc_scatt heavy nu-inelastic")
+    assert_parity(inel, ri, what="C++ calc_scatt heavy inelastic")
+    assert_parity(nu, rnu, what="C++ calc_scatt heavy nu-inelastic")
 
 
 @pytest.mark.gpu
