@@ -18,9 +18,17 @@ continuum, P0-P7, 70 groups, 20 000 E_in points).  One evaluation = one output e
             the CPU oracle (restatement of the reference algorithm; the image has no Fortran compiler)
             on all host cores, on a bounded sample of the same E_in grids.
 
-N > 1 (torchrun, one rank per GPU): weak scaling -- every rank integrates its own nuclide of the same
-shape (different seed), i.e. the library is sharded by nuclide; the moment arrays are gathered to
-rank 0 over NCCL inside the timed region, as the reference's driver needs them before output.
+N > 1 (torchrun, one rank per GPU): STRONG scaling of the same nuclide -- its E_in grids are dealt cyclically
+over the GPUs inside libndppgpu.so (ndppgpu_group_*, csrc/group.cuh), every rank integrates its columns, and the
+columns are gathered to the root device with ncclSend / ncclRecv on a side stream (two result buffers in turn,
+so the gather overlaps the next step's kernels).  torch.distributed only carries the NCCL id, the barrier and the
+max over ranks.  `e2e` at N > 1 includes the table uploads on every GPU, the gather and the D2H on the root.
+
+extra.configs     C1, C3 (293.6 / 600 / 1200 K), C4 (discrete, continuous, 16-bin histogram): evals/s, kernel ms,
+                  roofline fraction from the algorithmic work of SURVEY 8d, sampled CPU rate (N = 1)
+extra.c5_library  the 300-nuclide library (BASELINE configs[4]) through ndppgpu_plan_library / ndppgpu_library_run
+                  on the same N GPUs: seconds, evals/s, measured and modelled imbalance
+extra.strong_scaling_breakdown   per-rank kernel time against the step (N > 1)
 """
 from __future__ import annotations
 
@@ -51,6 +59,8 @@ def parse():
     ap.add_argument("--n-grid", type=int, default=20000, help="E_in points of the C2 nuclide (default: the named 20k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="E_in points in the CPU sample (0 = auto)")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.configs (C1, C3, C4) and extra.c5_library")
+    ap.add_argument("--c5-nuclides", type=int, default=300, help="nuclides of the C5 library in extra.c5_library")
     return ap.parse_args()
 
 
@@ -65,8 +75,9 @@ def workload_config(nuc, e_bins, params, Ein_el, Ein_inel, n_gpus):
     return {"workload": "C2 U-238-shape synthetic ACE nuclide: elastic + 40 levels (law 3) + continuum (law 44, CM)",
             "groups": len(e_bins) - 1, "legendre_orders": params.order + 1, "mu_bins": params.mu_bins,
             "ne_per_grp": params.ne_per_grp, "NE_elastic": int(len(Ein_el)), "NE_inelastic": int(len(Ein_inel)),
-            "reactions": len(nuc.reactions), "nuclides": n_gpus,
-            "parallelism": f"nuclide-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
+            "reactions": len(nuc.reactions), "nuclides": 1,
+            "parallelism": (f"one nuclide, E_in dealt cyclically over {n_gpus} GPUs inside libndppgpu.so (ndppgpu_group_*), "
+                            "NCCL gather to the root on a side stream") if n_gpus > 1 else "single GPU",
             "l2": "flushed between steps (256 MiB write)"}
 
 
@@ -193,7 +204,7 @@ def run_reference(args):
     value = float(np.sum([v * s for v, s in zip(vals, secs)]) / np.sum(secs))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(nuc, e_bins, params, Ein_el, Ein_inel, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,11 +213,23 @@ def run_reference(args):
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------
+def _flush_cost(torch, lib_stream, flush, steps):
+    with torch.cuda.stream(lib_stream):
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(lib_stream)
+        for _ in range(steps):
+            flush.fill_(0.0)
+        f1.record(lib_stream)
+    torch.cuda.synchronize()
+    return f0.elapsed_time(f1)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from ndpp_b200 import scatt
+    from ndpp_b200 import library, scatt
     from ndpp_b200.capi import Context
+    from ndpp_b200.group import Group, GroupNuclide
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,46 +238,52 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    group = None
     if world > 1:
+        # torch.distributed carries only what an MPI driver would carry over MPI: the NCCL id, the barrier and the
+        # max over ranks of the timings.  Sharding, NCCL communicator and gather are the library's (csrc/group.cuh).
         dist.init_process_group("nccl", device_id=dev)
+        group = Group.from_rank(local, rank, world, library.broadcast_id(dist, dev))
+        ctx = group.ctx(0)
+    else:
+        ctx = Context(local)
 
-    nuc, e_bins, params, Ein_el, Ein_inel = make_workload(args.n_grid, seed_offset=rank)
-    ctx = Context(local)
+    nuc, e_bins, params, Ein_el, Ein_inel = make_workload(args.n_grid)      # the same nuclide on every rank
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     GL = (len(e_bins) - 1) * (params.order + 1)
     ev_step = evals_per_step(e_bins, params, Ein_el, Ein_inel)
-
-    # device-resident state
-    dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
-    d_Eel = torch.from_numpy(Ein_el).to(dev)
-    d_Ein = torch.from_numpy(Ein_inel).to(dev)
     n_el, n_in = len(Ein_el), len(Ein_inel)
-    max_el, max_in = n_el, n_in
-    if world > 1:
-        # the ranks' nuclides have the same shape but np.unique may drop a duplicate grid point on some
-        # of them: pad every slab to the largest so that one NCCL gather per matrix assembles them
-        sizes = torch.tensor([n_el, n_in], device=dev)
-        dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
-        max_el, max_in = int(sizes[0]), int(sizes[1])
-    d_el_pad = torch.zeros((max_el, GL), dtype=torch.float64, device=dev)
-    d_inel_pad = torch.zeros((max_in, GL), dtype=torch.float64, device=dev)
-    d_el, d_inel = d_el_pad[:n_el], d_inel_pad[:n_in]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-    gather_el = gather_in = None
-    if world > 1 and rank == 0:
-        gather_el = [torch.empty_like(d_el_pad) for _ in range(world)]
-        gather_in = [torch.empty_like(d_inel_pad) for _ in range(world)]
 
-    def step_device():
-        with torch.cuda.stream(lib_stream):
-            flush.fill_(0.0)
-        dn.elastic_dev(d_Eel, d_el)
-        dn.inelastic_dev(d_Ein, d_inel)
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(lib_stream)
-            dist.gather(d_el_pad, gather_el, dst=0)
-            dist.gather(d_inel_pad, gather_in, dst=0)
-            lib_stream.wait_stream(torch.cuda.current_stream())
+    if world == 1:
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        d_Eel = torch.from_numpy(Ein_el).to(dev)
+        d_Ein = torch.from_numpy(Ein_inel).to(dev)
+        d_el = torch.zeros((n_el, GL), dtype=torch.float64, device=dev)
+        d_inel = torch.zeros((n_in, GL), dtype=torch.float64, device=dev)
+
+        def step_device():
+            with torch.cuda.stream(lib_stream):
+                flush.fill_(0.0)
+            dn.elastic_dev(d_Eel, d_el)
+            dn.inelastic_dev(d_Ein, d_inel)
+
+        def join():
+            pass
+    else:
+        # strong scaling: the E_in grids of the one nuclide dealt cyclically over the GPUs; every step ends with the
+        # NCCL gather of the columns to the root device, issued on a side stream with two result buffers in turn, so
+        # that it overlaps the kernels of the next step
+        gn = GroupNuclide(nuc, e_bins, params, group)
+        gn.set_grids(Ein_el, Ein_inel)
+
+        def step_device():
+            with torch.cuda.stream(lib_stream):
+                flush.fill_(0.0)
+            gn.integrate(3)
+
+        def join():
+            gn.join()
 
     def timed(fn, steps):
         torch.cuda.synchronize()
@@ -265,11 +294,11 @@ def run_b200(args):
         e0.record(lib_stream)
         for _ in range(steps):
             fn()
-        torch.cuda.current_stream().wait_stream(lib_stream)
-        lib_stream.wait_stream(torch.cuda.current_stream())
+        join()                      # the last gather and assembly lie inside the event bracket
         e1.record(lib_stream)
         torch.cuda.synchronize()
         if world > 1:
+            gn.sync()
             dist.barrier()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
@@ -281,7 +310,10 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step_device()
+    join()
     torch.cuda.synchronize()
+    if world > 1:
+        gn.sync()
     ctx.stats(reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
@@ -289,31 +321,50 @@ def run_b200(args):
     ms, wall = timed(step_device, args.steps)
     st = ctx.stats(reset=True)
     clk = clocks.stop() if rank == 0 else None
-    # the flush kernel is inside the event bracket: subtract its measured cost
-    with torch.cuda.stream(lib_stream):
-        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-        f0.record(lib_stream)
-        for _ in range(args.steps):
-            flush.fill_(0.0)
-        f1.record(lib_stream)
-    torch.cuda.synchronize()
-    flush_ms = f0.elapsed_time(f1)
+    flush_ms = _flush_cost(torch, lib_stream, flush, args.steps)    # the flush is inside the event bracket: subtract it
     ms_step = (ms - flush_ms) / args.steps
-    value = world * ev_step / (ms_step * 1e-3)
+    value = ev_step / (ms_step * 1e-3)          # whole job: one nuclide, whatever the number of GPUs
 
-    # ---- e2e: calc_scatt with host (pinned) buffers ----------------------------------------------
-    # page-locked host buffers for the E_in grids and the result matrices (the contract's e2e path)
+    breakdown = None
+    if world > 1:
+        # per-phase picture of a step, per rank: what the device did (CUDA-event kernel time) against the step
+        mine = torch.tensor([st["kernel_ms"] / args.steps, st["file6_cm_ms"] / args.steps, st["host_call_ms"] / args.steps,
+                             st["host_sync_ms"] / args.steps, float(st["launches"]) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = [a.tolist() for a in allr]
+        k = [a[0] for a in allr]
+        breakdown = {"ms_per_step": ms_step, "kernel_ms_per_rank": k, "file6_cm_ms_per_rank": [a[1] for a in allr],
+                     "host_call_ms_per_rank": [a[2] for a in allr], "host_sync_ms_per_rank": [a[3] for a in allr],
+                     "launches_per_rank": [a[4] for a in allr],
+                     "kernel_imbalance": max(k) / (sum(k) / world),
+                     "ms_outside_kernels_slowest_rank": ms_step - max(k),
+                     "gathered_bytes_per_step": group.gathered_bytes() / (args.steps + args.warmup) if rank == 0 else None,
+                     "note": "kernel_ms = CUDA-event time of the integrator kernels of a rank (they run back to back on "
+                             "one stream); ms_per_step - max(kernel_ms) = launch gaps, host read-backs (n_act, error "
+                             "latch) and whatever of the gather is not hidden behind the next step"}
+
+    # ---- e2e: the reference-facing call with HOST buffers ----------------------------------------------------------
     h_Eel = torch.from_numpy(Ein_el).pin_memory().numpy()
     h_Ein = torch.from_numpy(Ein_inel).pin_memory().numpy()
-    h_el = torch.empty((len(Ein_el), GL), dtype=torch.float64).pin_memory().numpy()
-    h_inel = torch.empty((len(Ein_inel), GL), dtype=torch.float64).pin_memory().numpy()
+    h_el = torch.empty((n_el, GL), dtype=torch.float64).pin_memory().numpy() if rank == 0 else None
+    h_inel = torch.empty((n_in, GL), dtype=torch.float64).pin_memory().numpy() if rank == 0 else None
 
-    def step_e2e():
-        dn2 = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
-        el = dn2.elastic(h_Eel, out=h_el)
-        inel, _ = dn2.inelastic(h_Ein, False, out=h_inel)
-        dn2.clear()
-        return el, inel
+    if world == 1:
+        def step_e2e():
+            dn2 = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+            dn2.elastic(h_Eel, out=h_el)
+            dn2.inelastic(h_Ein, False, out=h_inel)
+            dn2.clear()
+        e2e_call = "ndpp_b200.scatt.DeviceNuclide(...) + elastic(host) + inelastic(host) == calc_scatt"
+    else:
+        def step_e2e():   # table upload + convert_distro on every GPU, deal of the grids, integration, NCCL gather, D2H on the root
+            g2 = GroupNuclide(nuc, e_bins, params, group)
+            g2.elastic(h_Eel, out=h_el)
+            g2.inelastic(h_Ein, out=h_inel)
+            g2.clear()
+        e2e_call = ("ndpp_b200.group.GroupNuclide(...) + elastic(host) + inelastic(host) == calc_scatt on the device group "
+                    "(ndppgpu_group_*: includes the NCCL gather and the D2H of the assembled matrices on the root)")
 
     step_e2e()
     ctx.stats(reset=True)
@@ -330,25 +381,23 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     st2 = ctx.stats(reset=True)
-    e2e_value = world * ev_step * args.steps / e2e_s
+    if world > 1:   # bytes over PCIe, all ranks
+        t = torch.tensor([st2["h2d_bytes"], st2["d2h_bytes"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        st2["h2d_bytes"], st2["d2h_bytes"] = float(t[0]), float(t[1])
+    e2e_value = ev_step * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     flops, n_act = file6_cm_flops(nuc, e_bins, params, Ein_inel)
     f6_ms = st["file6_cm_ms"] / max(1, st["file6_cm_launches"])
     peak = ctx.measure_fp64_peak(0.5)
+    if world > 1:       # this rank integrated every world-th column
+        flops /= world
     achieved = flops / (f6_ms * 1e-3) / 1e12 if f6_ms > 0 else 0.0
-    traffic, ncu_extra = None, None
-    try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        if args.n_grid == 20000:
-            traffic = tj["traffic_bytes_per_launch"]
-            ncu_extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "achieved_occupancy_pct", "issue_slots_busy_pct",
-                                            "duration_ms_under_ncu", "fp64_issue_floor_ms", "source") if k in tj}
-    except Exception:
-        pass
+    traffic, ncu_extra = ncu_traffic(args)
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-            "kernel": "k_file6_cm_ws (integrate_file6_cm_leg: records + tables + pipeline kernel)",
+            "kernel": "k_file6_cm_ws (integrate_file6_cm_leg: records + tables + pipeline kernel)" + (" on rank 0" if world > 1 else ""),
             "kernel_ms": f6_ms, "kernel_share_of_step": f6_ms / ms_step if ms_step else None,
             "algorithmic_flops_per_launch": flops, "active_E_in": n_act,
             "peak_source": "measured in this run: ndppgpu_measure_fp64_peak (DFMA chains, all SMs); "
@@ -369,20 +418,178 @@ def run_b200(args):
         v, s, desc = cpu_run(nuc, e_bins, params, Ein_el, Ein_inel, args.cpu_sample or 1200, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "seconds": s}
 
+    # ---- extras: the other BASELINE configurations under the driver's clock ------------------------------------------
+    extra = {}
+    if not args.no_extras:
+        if world == 1:
+            dn.clear()
+            extra["configs"] = run_configs(ctx, peak, sample_cpu=not args.no_cpu_baseline)
+            cgroup = Group(1, devices=[local])
+            extra["c5_library"] = library.run_c5(cgroup, args.c5_nuclides)
+            cgroup.close()
+        else:
+            gn.clear()
+            extra["c5_library"] = library.run_c5(group, args.c5_nuclides, dist=dist, device=dev)
+        if breakdown:
+            extra["strong_scaling_breakdown"] = breakdown
+
     if rank == 0:
+        cfg = workload_config(nuc, e_bins, params, Ein_el, Ein_inel, world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(nuc, e_bins, params, Ein_el, Ein_inel, world),
-                "clocks": clk,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] / args.steps,
-                        "d2h_bytes_per_step": st2["d2h_bytes"] / args.steps,
-                        "call": "ndpp_b200.scatt.DeviceNuclide(...) + elastic(host) + inelastic(host) == calc_scatt"},
+                        "d2h_bytes_per_step": st2["d2h_bytes"] / args.steps, "call": e2e_call},
                 "gpu_launches": int(st["launches"]), "roofline": roof, "cpu_baseline": cpu,
-                "wall_s_timed_region": wall, "flush_ms_subtracted": flush_ms}
+                "wall_s_timed_region": wall, "flush_ms_subtracted": flush_ms, "extra": extra}
         print(json.dumps(line))
     if world > 1:
+        group.close()
         dist.destroy_process_group()
+
+
+def ncu_traffic(args):
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this workload.  The
+    capture names the kernel source it was taken on (sha256 of csrc/kernels_file6_ws.cuh); when the source has changed
+    since, the figure is reported as stale instead of being passed off as current."""
+    import hashlib
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+        if args.n_grid != 20000:
+            return None, None
+        src = os.path.join(ROOT, "ndpp_b200", "csrc", "kernels_file6_ws.cuh")
+        sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+        extra = {k: tj[k] for k in ("fp64_pipe_active_pct", "achieved_occupancy_pct", "issue_slots_busy_pct",
+                                    "duration_ms_under_ncu", "fp64_issue_floor_ms", "source") if k in tj}
+        extra["capture"] = "profiles/" + name
+        extra["kernel_source_sha16"] = sha
+        extra["stale"] = tj.get("kernel_source_sha16") != sha
+        return (None if extra["stale"] else tj["traffic_bytes_per_launch"]), extra
+    return None, None
+
+
+# ---- the other configurations (C1, C3 x 3 temperatures, C4 x 3) on one GPU -------------------------------------------------
+def _cpu_rate_nuclide(nuc, e_bins, params, Ein_el, Ein_inel, n, threads, counters=False):
+    """Oracle rate on n evenly spread E_in of each grid (rank 0, bounded)."""
+    from oracle import pyoracle
+    pyoracle.lib().ref_set_omp_chunk(1)
+    rn = pyoracle.RefNuclide(nuc, e_bins, params)
+    rn.convert_distro()
+    top = e_bins[-1]
+    pick = lambda E: E[E <= top][:: max(1, len(E[E <= top]) // n)][:n]
+    if counters:
+        pyoracle.freegas_counters(reset=True)
+    t0 = time.perf_counter()
+    ev = rn.elastic(pick(Ein_el), n_threads=threads).size
+    if Ein_inel is not None and len(Ein_inel):
+        a, b = rn.inelastic(pick(Ein_inel), n_threads=threads)
+        ev += a.size + (b.size if b is not None else 0)
+    dt = time.perf_counter() - t0
+    cnt = pyoracle.freegas_counters(reset=True) if counters else None
+    rn.close()
+    return ev / dt, len(pick(Ein_el)), cnt
+
+
+def run_configs(ctx, peak_tflops, sample_cpu=True):
+    """evals/s, kernel time, roofline fraction (algorithmic flops of SURVEY 8d / CUDA-event kernel time / measured FP64
+    peak; HBM GB/s for the memory-bound stage 2 of the continuous S(a,b) path) and the sampled CPU rate of every
+    BASELINE configuration that is not the headline one.  Second pass of each (the first loads kernels and grows the pool)."""
+    from ndpp_b200 import ace, egrid, scatt, synth
+    threads = os.cpu_count() or 1
+    rows = []
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        hbm_peak = None
+
+    def nuclide_row(name, nuc, e_bins, params, Eel, Einel, flops, n_cpu, flop_note, counters=False):
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        for _ in range(2):
+            ctx.stats(reset=True)
+            t0 = time.perf_counter()
+            el = dn.elastic(Eel)
+            inel = dn.inelastic(Einel) if Einel is not None else None
+            wall = time.perf_counter() - t0
+        st = ctx.stats(reset=True)
+        dn.clear()
+        ev = el.size + (sum(x.size for x in inel if x is not None) if inel is not None else 0)
+        row = {"config": name, "evals": int(ev), "evals_per_s_e2e": ev / wall, "kernel_ms": st["kernel_ms"],
+               "evals_per_s_kernel": ev / (st["kernel_ms"] * 1e-3), "launches": int(st["launches"])}
+        cnt = None
+        if sample_cpu:
+            rate, n, cnt = _cpu_rate_nuclide(nuc, e_bins, params, Eel, Einel, n_cpu, threads, counters)
+            row["cpu"] = {"evals_per_s": rate, "cores": threads, "kind": "port", "sample": f"{n} evenly spread E_in per grid"}
+        f = flops(cnt) if callable(flops) else flops
+        if f:
+            row["roofline"] = {"bound": "fp64", "algorithmic_flops": f, "achieved": f / (st["kernel_ms"] * 1e-3) / 1e12,
+                               "peak": peak_tflops, "unit": "TFLOP/s", "frac": f / (st["kernel_ms"] * 1e-3) / 1e12 / peak_tflops,
+                               "formula": flop_note}
+        return row
+
+    # C1: tests/test_scatt fixture
+    nuc, e_bins, params = synth.c1_fixture()
+    Ein = synth.c1_ein_grid(997)
+    G, L, M = len(e_bins) - 1, params.order + 1, params.mu_bins
+    FA = 12 + 22 * G + 40 * 2 + (M + 2) * (13 + 4 * (L - 2) + 10 * L)
+    FC = 2 * M * (13 + 2 * G) + G * (M - 1) * (15 * L + 11)
+    rows.append(nuclide_row("C1 tests/test_scatt fixture (MT 51/52 relabelled), 1000 E_in", nuc, e_bins, params, Ein, Ein,
+                            float(len(Ein) * (2 * FA + 2 * FA + FC)), 200,
+                            "per E_in: F_A (elastic) + F_A (CM level) + F_C (lab Law 44), M_act = M"))
+    # C3: H-1 free gas at three temperatures
+    for kT, T in ((synth.KT_293K, 293.6), (synth.KT_600K, 600), (synth.KT_1200K, 1200)):
+        nuc, e_bins, params, Ein = synth.c3_h1_freegas(kT=kT)
+        L = params.order + 1
+        n_cpu = 12
+        fl = (lambda cnt, NE=len(Ein), n=n_cpu, L=L: float(NE / n * (40.0 * cnt[0] + 35.0 * cnt[1] + 4.0 * (L - 2) * cnt[0]))
+              if cnt else None)
+        rows.append(nuclide_row(f"C3 H-1 free gas {T} K, P3, 70 groups, 1000 E_in", nuc, e_bins, params, Ein, None, fl, n_cpu,
+                                "F_E = 40 N_fgk + 35 N_sab + 4(L-2) N_fgk, N counted by the instrumented oracle on the CPU "
+                                "sample and scaled to the grid", counters=True))
+    # C4: S(a,b)
+    e_bins = synth.group_structure(70)
+    G = len(e_bins) - 1
+    for name, sab, tab in (("C4 H-in-H2O S(a,b) discrete (skewed), P5", synth.c4_sab("skewed"), False),
+                           ("C4 H-in-H2O S(a,b) continuous, P5", synth.c4_sab("cont", n_eout=400), False),
+                           ("C4 H-in-H2O S(a,b) discrete (skewed), 16-bin cosine histogram", synth.c4_sab("skewed"), True)):
+        Ein = egrid.sab_egrid(sab, e_bins)
+        order = 16 if tab else 5
+        L = order if tab else order + 1
+        ds = scatt.DeviceSab(sab, ctx)
+        for _ in range(2):
+            ctx.stats(reset=True)
+            t0 = time.perf_counter()
+            got = ds.calc(e_bins, ace.SCATT_TYPE_TABULAR if tab else ace.SCATT_TYPE_LEGENDRE, order, Ein)
+            wall = time.perf_counter() - t0
+        st = ctx.stats(reset=True)
+        ds.clear()
+        row = {"config": name, "evals": int(got.size), "evals_per_s_e2e": got.size / wall, "kernel_ms": st["kernel_ms"],
+               "evals_per_s_kernel": got.size / (st["kernel_ms"] * 1e-3), "launches": int(st["launches"]), "NE": len(Ein)}
+        n_mu = sab.n_inelastic_mu
+        if sab.secondary_mode == ace.SAB_SECONDARY_CONT:
+            f1 = sum((len(d.e_out) + 2 * G) * n_mu * (4 * (L - 2) + 2 * L) for d in sab.inelastic_data)
+            by = 24.0 * G * L * len(Ein)
+            row["roofline"] = {"bound": "hbm", "algorithmic_bytes": by, "achieved": by / (st["kernel_ms"] * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": by / (st["kernel_ms"] * 1e-3) / 1e9 / hbm_peak if hbm_peak else None,
+                               "formula": "stage 2: 24 G L bytes per E_in (stage 1: %.3g flop once)" % f1,
+                               "note": "launch-bound at this size: 5 kernels over %d E_in" % len(Ein)}
+        else:
+            f = float(len(Ein) * sab.n_inelastic_e_out * (17 + n_mu * (3 + 4 * (L - 2) + 2 * L)))
+            row["roofline"] = {"bound": "fp64", "algorithmic_flops": f, "achieved": f / (st["kernel_ms"] * 1e-3) / 1e12,
+                               "peak": peak_tflops, "unit": "TFLOP/s", "frac": f / (st["kernel_ms"] * 1e-3) / 1e12 / peak_tflops,
+                               "formula": "F_F = NEo (17 + n_mu (3 + 4(L-2) + 2L)) per E_in",
+                               "note": "launch-bound at this size: 4 kernels over %d E_in" % len(Ein)}
+        if sample_cpu:
+            from oracle import pyoracle
+            idx = np.arange(len(Ein))[:: max(1, len(Ein) // 400)]
+            t0 = time.perf_counter()
+            ref = pyoracle.sab_calc(sab, e_bins, order, Ein[idx], tabular=tab)
+            row["cpu"] = {"evals_per_s": ref.size / (time.perf_counter() - t0), "cores": 1, "kind": "port",
+                          "sample": f"{len(idx)} evenly spread E_in"}
+        rows.append(row)
+    return rows
 
 
 def main():

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NDPPGPU_ABI_VERSION 1
+#define NDPPGPU_ABI_VERSION 2
 
 /* run-time integration parameters: src/global.F90:28-59, defaults src/constants.F90:69-100 */
 typedef struct {
@@ -222,6 +222,109 @@ int ndppgpu_eval_libm(void *ctx, int fn, const double *x, long long n, double *y
 
 int ndppgpu_test_legendre(void *ctx, int n, int L, const double *xlow, const double *xhigh, const double *flow,
                           const double *fhigh, double *integrals, double *pn);
+
+/* ==== several GPUs =====================================================================================
+ * Replaces the reference's own distribution of a library: partition_work (static contiguous blocks of nuclides per
+ * MPI rank, src/ndpp.F90:934-950), the nuclide loop (:549) and the hand-back of the results (:839-864).
+ *
+ * A *group* is the set of GPUs that work together: every GPU of this process (ndppgpu_group_init: one host thread per
+ * device inside the library, ncclCommInitAll) or one GPU per process (ndppgpu_group_init_rank: ncclCommInitRank with
+ * an id made by ndppgpu_group_unique_id on rank 0 and broadcast by the caller, e.g. MPI_Bcast).  Global rank 0 is the
+ * root: it receives the assembled matrices.  In the one-GPU-per-process form every ndppgpu_group_* / ndppgpu_library_*
+ * call is collective (all ranks, same arguments); result arrays may be NULL on the other ranks.
+ * NCCL is loaded on demand (libnccl.so.2, or $NDPPGPU_NCCL_LIB); a group of one device needs none. */
+int ndppgpu_group_init(int n_devices /* <= 0: all */, const int *devices /* NULL: 0..n-1 */, void **group);
+int ndppgpu_group_unique_id(void *id128 /* 128 bytes out */);
+int ndppgpu_group_init_rank(int device, int rank, int world, const void *id128, void **group);
+int ndppgpu_group_info(void *group, int *world, int *n_local, int *first_rank);
+/* borrowed context of a local device (ndppgpu_stats, ndppgpu_stream); owned by the group */
+void *ndppgpu_group_ctx(void *group, int local_index);
+/* bytes the root received over NCCL since the last reset */
+long long ndppgpu_group_gathered_bytes(void *group, int reset);
+int ndppgpu_group_finalize(void *group);
+
+/* A nuclide replicated on every device of the group; same arguments as ndppgpu_nuclide_create / _add_reaction /
+ * ndppgpu_convert_distro / ndppgpu_elastic / ndppgpu_inelastic.  The E_in grid is dealt cyclically over the devices
+ * (column i to device i mod N), every device integrates its columns, the columns are gathered to the root device with
+ * ncclSend / ncclRecv over NVLink, put back in order, and the top-of-grid rule (src/scatt.F90:669,770) is applied on
+ * the root.  The matrices equal the one-device call's bit for bit. */
+int ndppgpu_group_nuclide_create(void *group, double awr, double kT, double freegas_cutoff, int n_grid,
+                                 const double *energy, const double *elastic_xs, const double *e_bins, int n_bins,
+                                 const ndppgpu_params *params, void **gnuc);
+int ndppgpu_group_nuclide_add_reaction(void *gnuc, int rxn_index, int MT, double Q_value, int threshold,
+                                       int scatter_in_cm, int has_angle_dist, int has_energy_dist, int law,
+                                       int multiplicity, const double *yield_tab1, int n_yield, const double *sigma,
+                                       int n_sigma, const double *p_valid_tab1, int n_pvalid,
+                                       const double *adist_energy, const int *adist_type, const int *adist_loc,
+                                       int n_adist_e, const double *adist_data, int n_adist_data,
+                                       const double *edist_data, int n_edist_data);
+int ndppgpu_group_convert_distro(void *gnuc);
+int ndppgpu_group_elastic(void *gnuc, const double *Ein, int NE, double *el_mat /* root */);
+int ndppgpu_group_inelastic(void *gnuc, const double *Ein, int NE, double *inel_mat, double *nuinel_mat /* root */);
+int ndppgpu_group_nuclide_free(void *gnuc);
+/* The same in pieces, for callers that keep grids and results on the devices: set_grids deals and uploads the grids once
+ * (a negative count leaves that grid as it is); integrate (what = 1 elastic, 2 inelastic, 3 both) only
+ * enqueues -- kernels on every device's stream, the gather and the assembly on side streams, two result buffers in
+ * turn, so the gather of one call overlaps the kernels of the next; sync waits; fetch copies the latest assembled
+ * matrices to host arrays on the root; result_dev is their device address on the root device (0 elastic, 1 inelastic,
+ * 2 nu-inelastic), valid until the second next integrate. */
+int ndppgpu_group_set_grids(void *gnuc, const double *Ein_el, int NE_el, const double *Ein_inel, int NE_inel);
+int ndppgpu_group_integrate(void *gnuc, int what);
+int ndppgpu_group_sync(void *gnuc);
+/* device-side join: each device's stream (ndppgpu_stream of its context) waits for the gathers enqueued so far */
+int ndppgpu_group_join(void *gnuc);
+int ndppgpu_group_fetch(void *gnuc, double *el_mat, double *inel_mat, double *nuinel_mat);
+void *ndppgpu_group_result_dev(void *gnuc, int matrix);
+
+/* ---- a whole library: work items (nuclide, matrix, E_in tile), cost-weighted, longest-processing-time-first ------------
+ * ndppgpu_plan_library is host code (no GPU needed).  A shape is what the cost model needs to know of a nuclide; the
+ * cost of a tile is the algorithmic-flop count of SURVEY 8d (F_A per open level, F_B for the CM continuum, the counted
+ * F_E per free-gas column) with E_in taken log-uniform between e_lo and e_hi -- it steers the balance only, never a
+ * result.  policy 0: LPT with setup_cost (model flops) charged per (device, nuclide) opened; policy 1: the reference's
+ * static contiguous blocks of nuclides.  Items come back sorted by (rank, nuclide, matrix, tile). */
+typedef struct {
+    int index;                      /* caller's nuclide number */
+    int n_el, n_inel;               /* E_in points of the two grids */
+    int n_levels;                   /* discrete levels (file-4 CM integrations) */
+    int has_cont;                   /* Law 44 / 61 continuum in the CM frame (file-6 CM) */
+    int freegas_points;             /* elastic E_in below the free-gas cutoff */
+    double cont_threshold, e_lo, e_hi;
+    const double *level_thresholds; /* [n_levels] MeV */
+} ndppgpu_shape;
+typedef struct {
+    int nuclide, matrix /* 0 elastic, 1 inelastic */, tile, n_tiles, rank;
+    int rows;                       /* E_in points of the tile: ndppgpu_tile_bounds(NE, tile, n_tiles) (set by the caller) */
+    double cost;
+} ndppgpu_item;
+int ndppgpu_plan_library(const ndppgpu_shape *shapes, int n_shapes, int G, int L, int M, int K, int tile_rows, int world,
+                         double setup_cost, int policy, ndppgpu_item *items_out, int max_items, int *n_items,
+                         double *imbalance /* max device load / mean */);
+void ndppgpu_tile_bounds(int n, int tile, int n_tiles, int *lo, int *hi);
+
+/* Runs a plan.  Every device walks its items; when it meets a new nuclide it calls open(user, nuclide, ctx, ...) -- the
+ * caller parses / builds that nuclide on the given context (ndppgpu_nuclide_create + _add_reaction; convert_distro is
+ * called by the library if the caller has not) and returns the handle and its two E_in grids -- integrates the tiles in
+ * place into one result buffer per device, and calls close (NULL: ndppgpu_nuclide_free).  open / close are called from
+ * the device's worker thread.  Then one NCCL gather brings every buffer to the root device, where ndppgpu_library_fetch
+ * assembles a matrix (0 elastic, 1 inelastic, 2 nu-inelastic) of a nuclide into a host array. */
+typedef int (*ndppgpu_open_fn)(void *user, int nuclide, void *ctx, void **nuc, const double **Ein_el, int *NE_el,
+                               const double **Ein_inel, int *NE_inel);
+typedef int (*ndppgpu_close_fn)(void *user, int nuclide, void *nuc);
+typedef struct {
+    double wall_s, compute_s, gather_s;      /* host wall time: all, until the slowest device finished, the gather */
+    double open_s_max, integrate_s_max;      /* slowest local device: opening nuclides / integrating tiles */
+    double kernel_s_max, kernel_s_sum;       /* CUDA-event kernel time: slowest local device, sum over local devices */
+    long long moment_evals;                  /* whole plan */
+    int items, opens;                        /* items of the plan; nuclides opened by the local devices */
+    double device_s_max;                     /* CUDA-event time from a device's first upload to the end of its part of the
+                                                gather, slowest local device */
+    double reserved[3];
+} ndppgpu_library_report;
+int ndppgpu_library_create(void *group, int G, int L, int nuscatter, const ndppgpu_item *items, int n_items, void **lib);
+int ndppgpu_library_run(void *lib, ndppgpu_open_fn open, ndppgpu_close_fn close, void *user, ndppgpu_library_report *rep);
+int ndppgpu_library_fetch(void *lib, int nuclide, int matrix, const double *Ein, int NE, double e_top, double *mat);
+int ndppgpu_library_report_get(void *lib, ndppgpu_library_report *rep);
+int ndppgpu_library_free(void *lib);
 
 /* ---- device micro-benchmark: sustained FP64 FMA rate of this GPU, used as the roofline
  *      denominator (MEASURED_PEAKS.json holds no FP64 figure) ----------------------------------- */

@@ -26,7 +26,14 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_sab_free", "ndppgpu_measure_fp64_peak", "ndppgpu_interp_distro", "ndppgpu_test_legendre", "ndppgpu_nuclide_set_table",
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
            "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
-           "ndppgpu_inelastic_thinned", "ndppgpu_chi", "ndppgpu_eval_libm"]
+           "ndppgpu_inelastic_thinned", "ndppgpu_chi", "ndppgpu_eval_libm",
+           "ndppgpu_group_init", "ndppgpu_group_unique_id", "ndppgpu_group_init_rank", "ndppgpu_group_info",
+           "ndppgpu_group_ctx", "ndppgpu_group_gathered_bytes", "ndppgpu_group_finalize",
+           "ndppgpu_group_nuclide_create", "ndppgpu_group_nuclide_add_reaction", "ndppgpu_group_convert_distro",
+           "ndppgpu_group_elastic", "ndppgpu_group_inelastic", "ndppgpu_group_nuclide_free", "ndppgpu_group_set_grids",
+           "ndppgpu_group_integrate", "ndppgpu_group_sync", "ndppgpu_group_join", "ndppgpu_group_fetch", "ndppgpu_group_result_dev",
+           "ndppgpu_plan_library", "ndppgpu_tile_bounds", "ndppgpu_library_create", "ndppgpu_library_run",
+           "ndppgpu_library_fetch", "ndppgpu_library_report_get", "ndppgpu_library_free"]
 
 
 class NdppGpuError(RuntimeError):
@@ -48,6 +55,28 @@ class StatsC(C.Structure):
                 ("host_call_ms", C.c_double), ("host_alloc_ms", C.c_double), ("host_sync_ms", C.c_double),
                 ("freegas_items", C.c_longlong), ("reserved", C.c_double * 2)]
 
+
+class ShapeC(C.Structure):
+    _fields_ = [("index", C.c_int), ("n_el", C.c_int), ("n_inel", C.c_int), ("n_levels", C.c_int), ("has_cont", C.c_int),
+                ("freegas_points", C.c_int), ("cont_threshold", C.c_double), ("e_lo", C.c_double), ("e_hi", C.c_double),
+                ("level_thresholds", C.POINTER(C.c_double))]
+
+
+class ItemC(C.Structure):
+    _fields_ = [("nuclide", C.c_int), ("matrix", C.c_int), ("tile", C.c_int), ("n_tiles", C.c_int), ("rank", C.c_int),
+                ("rows", C.c_int), ("cost", C.c_double)]
+
+
+class LibraryReportC(C.Structure):
+    _fields_ = [("wall_s", C.c_double), ("compute_s", C.c_double), ("gather_s", C.c_double), ("open_s_max", C.c_double),
+                ("integrate_s_max", C.c_double), ("kernel_s_max", C.c_double), ("kernel_s_sum", C.c_double),
+                ("moment_evals", C.c_longlong), ("items", C.c_int), ("opens", C.c_int), ("device_s_max", C.c_double),
+                ("reserved", C.c_double * 3)]
+
+
+OPEN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_double)),
+                      C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int))
+CLOSE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 
 _lib = None
 
@@ -101,6 +130,37 @@ def load() -> C.CDLL:
     L.ndppgpu_gather_columns_dev.argtypes = [vp, vp, vp, i, i, vp]
     L.ndppgpu_elastic_thinned.argtypes = [vp, c_dp, i, d, d, c_dp, i, c_dp, c_ip, c_dp, c_dp]
     L.ndppgpu_inelastic_thinned.argtypes = [vp, c_dp, i, d, d, c_dp, i, c_dp, c_dp, c_ip, c_dp, c_dp]
+    # several GPUs (csrc/group.cuh)
+    L.ndppgpu_group_init.argtypes = [i, c_ip, C.POINTER(vp)]
+    L.ndppgpu_group_unique_id.argtypes = [vp]
+    L.ndppgpu_group_init_rank.argtypes = [i, i, i, vp, C.POINTER(vp)]
+    L.ndppgpu_group_info.argtypes = [vp, c_ip, c_ip, c_ip]
+    L.ndppgpu_group_ctx.argtypes = [vp, i]
+    L.ndppgpu_group_ctx.restype = vp
+    L.ndppgpu_group_gathered_bytes.argtypes = [vp, i]
+    L.ndppgpu_group_gathered_bytes.restype = C.c_longlong
+    L.ndppgpu_group_finalize.argtypes = [vp]
+    L.ndppgpu_group_nuclide_create.argtypes = [vp, d, d, d, i, c_dp, c_dp, c_dp, i, C.POINTER(ParamsC), C.POINTER(vp)]
+    L.ndppgpu_group_nuclide_add_reaction.argtypes = L.ndppgpu_nuclide_add_reaction.argtypes
+    L.ndppgpu_group_convert_distro.argtypes = [vp]
+    L.ndppgpu_group_elastic.argtypes = [vp, c_dp, i, c_dp]
+    L.ndppgpu_group_inelastic.argtypes = [vp, c_dp, i, c_dp, c_dp]
+    L.ndppgpu_group_nuclide_free.argtypes = [vp]
+    L.ndppgpu_group_set_grids.argtypes = [vp, c_dp, i, c_dp, i]
+    L.ndppgpu_group_integrate.argtypes = [vp, i]
+    L.ndppgpu_group_sync.argtypes = [vp]
+    L.ndppgpu_group_join.argtypes = [vp]
+    L.ndppgpu_group_fetch.argtypes = [vp, c_dp, c_dp, c_dp]
+    L.ndppgpu_group_result_dev.argtypes = [vp, i]
+    L.ndppgpu_group_result_dev.restype = vp
+    L.ndppgpu_plan_library.argtypes = [C.POINTER(ShapeC), i, i, i, i, i, i, i, d, i, C.POINTER(ItemC), i, c_ip, c_dp]
+    L.ndppgpu_tile_bounds.argtypes = [i, i, i, c_ip, c_ip]
+    L.ndppgpu_tile_bounds.restype = None
+    L.ndppgpu_library_create.argtypes = [vp, i, i, i, C.POINTER(ItemC), i, C.POINTER(vp)]
+    L.ndppgpu_library_run.argtypes = [vp, OPEN_FN, CLOSE_FN, vp, C.POINTER(LibraryReportC)]
+    L.ndppgpu_library_fetch.argtypes = [vp, i, i, c_dp, i, d, c_dp]
+    L.ndppgpu_library_report_get.argtypes = [vp, C.POINTER(LibraryReportC)]
+    L.ndppgpu_library_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -141,10 +201,14 @@ def check(rc, ctx=None):
 class Context:
     """One device context (ndppgpu_init / ndppgpu_finalize)."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, borrowed=None):
         self.lib = load()
         self.h = C.c_void_p()
-        check(self.lib.ndppgpu_init(int(device), C.byref(self.h)))
+        self.owned = borrowed is None
+        if borrowed is not None:           # a context that belongs to a device group (ndppgpu_group_ctx)
+            self.h = C.c_void_p(borrowed)
+        else:
+            check(self.lib.ndppgpu_init(int(device), C.byref(self.h)))
 
     def stats(self, reset=False) -> dict:
         s = StatsC()
@@ -181,7 +245,8 @@ class Context:
 
     def close(self):
         if self.h:
-            self.lib.ndppgpu_finalize(self.h)
+            if self.owned:
+                self.lib.ndppgpu_finalize(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

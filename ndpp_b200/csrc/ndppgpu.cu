@@ -79,8 +79,10 @@ struct DevBuf {  // owning device allocation (stream-ordered pool: no device-wid
     void* p = nullptr;
     size_t bytes = 0;
     cudaStream_t st = nullptr;
-    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    ~DevBuf() { reset(); }
+    void reset() { if (p) cudaFreeAsync(p, st); p = nullptr; bytes = 0; }
     DevBuf() = default;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), st(o.st) { o.p = nullptr; o.bytes = 0; }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     template <class T> T* as() const { return (T*)p; }
@@ -1781,3 +1783,5 @@ int ndppgpu_measure_fp64_peak(void* ctx, double seconds, double* tflops)
 }
 
 }  // extern "C"
+
+#include "group.cuh"

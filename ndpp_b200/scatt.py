@@ -26,6 +26,25 @@ def default_context() -> Context:
     return _default_ctx
 
 
+def reaction_args(nuc: Nuclide):
+    """The argument lists of ndppgpu_nuclide_add_reaction (after the handle) for every ScattData slot of a nuclide, in the
+    order calc_scatt fills rxn_data(:) (src/scatt.F90:88-105)."""
+    for idx, rxn, ed in iter_slots(nuc):
+        yt = f64(rxn.multiplicity_E.flatten()) if rxn.multiplicity_E is not None else None
+        sig = f64(rxn.sigma)
+        ad = rxn.adist
+        ae = at = al = adata = None
+        if ad is not None:
+            ae, at, al, adata = f64(ad.energy), i32(ad.type), i32(ad.location), f64(ad.data)
+        pv = f64(ed.p_valid.flatten()) if (ed is not None and ed.p_valid is not None) else None
+        edata = f64(ed.data) if ed is not None else None
+        yield (idx, rxn.MT, rxn.Q_value, rxn.threshold, int(rxn.scatter_in_cm), int(ad is not None),
+               int(ed is not None), ed.law if ed is not None else 0, rxn.multiplicity, dp(yt),
+               0 if yt is None else len(yt), dp(sig), len(sig), dp(pv), 0 if pv is None else len(pv), dp(ae), ip(at),
+               ip(al), 0 if ae is None else len(ae), dp(adata), 0 if adata is None else len(adata), dp(edata),
+               0 if edata is None else len(edata))
+
+
 class DeviceNuclide:
     """Device-resident ScattData set of one nuclide: what calc_scatt builds in rxn_data(:)
     (src/scatt.F90:84-126) -- scatt_init for every (reaction, energy distribution) slot followed by
@@ -44,21 +63,8 @@ class DeviceNuclide:
         check(self.lib.ndppgpu_nuclide_create(self.ctx.h, nuc.awr, nuc.kT, nuc.freegas_cutoff, len(en), dp(en), dp(el),
                                               dp(self.e_bins), len(self.e_bins), C.byref(pc), C.byref(self.h)),
               self.ctx.h)
-        for idx, rxn, ed in iter_slots(nuc):
-            yt = f64(rxn.multiplicity_E.flatten()) if rxn.multiplicity_E is not None else None
-            sig = f64(rxn.sigma)
-            ad = rxn.adist
-            ae = at = al = adata = None
-            if ad is not None:
-                ae, at, al, adata = f64(ad.energy), i32(ad.type), i32(ad.location), f64(ad.data)
-            pv = f64(ed.p_valid.flatten()) if (ed is not None and ed.p_valid is not None) else None
-            edata = f64(ed.data) if ed is not None else None
-            check(self.lib.ndppgpu_nuclide_add_reaction(
-                self.h, idx, rxn.MT, rxn.Q_value, rxn.threshold, int(rxn.scatter_in_cm), int(ad is not None),
-                int(ed is not None), ed.law if ed is not None else 0, rxn.multiplicity, dp(yt),
-                0 if yt is None else len(yt), dp(sig), len(sig), dp(pv), 0 if pv is None else len(pv), dp(ae), ip(at),
-                ip(al), 0 if ae is None else len(ae), dp(adata), 0 if adata is None else len(adata), dp(edata),
-                0 if edata is None else len(edata)), self.ctx.h)
+        for args in reaction_args(nuc):
+            check(self.lib.ndppgpu_nuclide_add_reaction(self.h, *args), self.ctx.h)
         self.n_slots = self.lib.ndppgpu_nuclide_n_slots(self.h)
         if convert:
             self.convert_distro()

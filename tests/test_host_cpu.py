@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ndppgpu.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert lib.ndppgpu_abi_version() == 1
+    assert lib.ndppgpu_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -152,30 +152,72 @@ def test_freegas_explicit_stack_matches_recursion(oracle):
 
 
 GLOO_SCRIPT = r'''
+# World-size-2 run of the host side of the one-process-per-GPU form (what an MPI driver does with MPI_Bcast /
+# MPI_Allreduce around the collective ndppgpu_group_* / ndppgpu_library_* calls), over gloo on the CPU.
 import os, sys
 sys.path.insert(0, os.environ["NDPP_ROOT"])
 import numpy as np, torch, torch.distributed as dist
-from ndpp_b200 import parallel
+from ndpp_b200 import group, library
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
+
+# 1. the NCCL id is made on rank 0 (ncclGetUniqueId needs no GPU) and reaches every rank unchanged
+nid = library.broadcast_id(dist)
+ids = [None] * world
+dist.all_gather_object(ids, nid)
+assert len(nid) == 128 and any(nid) and all(x == nid for x in ids)
+
+# 2. every rank derives the same plan from the shapes alone; each item has exactly one owner
+shapes = [library.NuclideShape(i, 900 + 37 * i, 300 + 11 * i, (0.1 * (i + 1),), 1.5 if i % 2 else None, 1e-11, 20.0)
+          for i in range(5)]
+items, imb = library.plan(shapes, 4, 3, 101, 5, world, tile_rows=256)
+plans = [None] * world
+dist.all_gather_object(plans, [(it["rank"], it["nuclide"], it["matrix"], it["tile"], it["n_tiles"]) for it in items])
+assert all(p == plans[0] for p in plans)
+assert len({(n, m, t) for _, n, m, t, _ in plans[0]}) == len(plans[0])
+assert {r for r, *_ in plans[0]} == set(range(world)) and 1.0 <= imb < 1.5
+
+# 3. the true grid sizes are known only to the rank that parsed a nuclide (they differ from the planner's estimates):
+#    after the exchange every rank holds all of them and the tile heights add up to the grids
+own = library.owners(items)
+true = {s.index: (s.n_el + 3 * s.index, s.n_inel + 5 + s.index) for s in shapes}
+sizes = library.exchange_sizes(dist, len(shapes), {i: true[i] for i in own.get(rank, set())})
+assert sizes == true
+library.set_rows(items, sizes)
+for s in shapes:
+    for m in (0, 1):
+        assert sum(it["rows"] for it in items if it["nuclide"] == s.index and it["matrix"] == m) == true[s.index][m]
+rows = [None] * world
+dist.all_gather_object(rows, [it["rows"] for it in items])
+assert all(r == rows[0] for r in rows)
+
+# 4. the cyclic deal of one nuclide's E_in grid (csrc/group.cuh: column i to device i mod N; the root puts column k of
+#    device r back at i = r + k N) and the top-of-grid rule applied after the assembly, because the predecessor of a
+#    column above the top group edge lives on another rank
 NE, GL = 1003, 12
 Ein = np.linspace(1.0, 3.0, NE); Ein[-1] = 3.003
-lo, hi = parallel.shard_range(NE, rank, world)
-assert parallel.shard_range(NE, 0, world)[0] == 0 and parallel.shard_range(NE, world - 1, world)[1] == NE
-local = torch.tensor(np.outer(Ein[lo:hi], np.arange(1, GL + 1)))      # stand-in for the moment slab
-local[Ein[lo:hi] > 3.0] = float("nan")                               # columns the copy rule must fill
-full = parallel.gather_columns(local, NE, dst=0)
+mine = Ein[rank::world]
+local = torch.tensor(np.outer(mine, np.arange(1, GL + 1)))       # stand-in for the moment columns of this rank
+local[mine > 3.0] = float("nan")                                 # the copy rule must fill these
+n_of = [(NE - r + world - 1) // world for r in range(world)]
+assert local.shape[0] == n_of[rank]
+pad = torch.zeros((max(n_of), GL), dtype=torch.float64); pad[:local.shape[0]] = local
+stage = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+dist.gather(pad, stage, dst=0)
 if rank == 0:
-    parallel.copy_top_columns(full, torch.tensor(Ein), 3.0)
+    full = np.stack([stage[i % world][i // world].numpy() for i in range(NE)])
+    for i in range(1, NE):
+        if not Ein[i] <= 3.0:
+            full[i] = full[i - 1]
     ref = np.outer(Ein, np.arange(1, GL + 1)); ref[-1] = ref[-2]
-    assert np.array_equal(full.numpy(), ref)
+    assert np.array_equal(full, ref)
     print("GLOO_OK")
 dist.destroy_process_group()
 '''
 
 
-def test_shard_and_gather_world_size_2_gloo(tmp_path):
-    script = tmp_path / "gloo_shard.py"
+def test_host_side_of_the_rank_form_world_size_2_gloo(tmp_path):
+    script = tmp_path / "gloo_host.py"
     script.write_text(GLOO_SCRIPT)
     env = dict(os.environ, NDPP_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
@@ -186,85 +228,33 @@ def test_shard_and_gather_world_size_2_gloo(tmp_path):
 
 
 def test_library_plan_balances_better_than_static_blocks():
-    """LPT over (nuclide, matrix, E_in tile) items vs the reference's contiguous nuclide blocks
-    (src/ndpp.F90:941-948) on the C5 shapes: every item is planned exactly once, the plan is
-    deterministic, and the modelled imbalance is far lower."""
-    from ndpp_b200 import library, synth
+    '''ndppgpu_plan_library (host code of libndppgpu.so, no GPU needed): LPT over (nuclide, matrix, E_in tile) items vs
+    the reference's contiguous nuclide blocks (src/ndpp.F90:941-948) on the C5 shapes: every item is planned exactly
+    once, the plan is deterministic, and the modelled imbalance is far lower.'''
+    from ndpp_b200 import group, library, synth
     specs = synth.c5_library(300)[:24]
     shapes = [synth.c5_shape(s) for s in specs]
-    items = library.make_items(shapes, 70, 6, 2001, 20)
     for world in (2, 8):
-        lpt, static = library.plan_lpt(items, world), library.plan_static_blocks(items, shapes, world)
-        assert sorted((i.nuclide, i.matrix, i.tile) for p in lpt for i in p) == \
-               sorted((i.nuclide, i.matrix, i.tile) for i in items)
-        assert lpt == library.plan_lpt(list(reversed(items)), world)
-        assert library.imbalance(lpt) < 1.10 and library.imbalance(lpt) <= library.imbalance(static)
-    assert library.imbalance(static) > 1.3   # 8 ranks, 24 nuclides: the static blocks are far off
-    lo = [library.tile_bounds(1003, t, 4) for t in range(4)]
+        lpt, imb = library.plan(shapes, 70, 6, 2001, 20, world)
+        static, imb_s = library.plan(shapes, 70, 6, 2001, 20, world, policy="static")
+        key = lambda it: (it["nuclide"], it["matrix"], it["tile"])
+        assert sorted(map(key, lpt)) == sorted(map(key, static)) and len(set(map(key, lpt))) == len(lpt)
+        again, _ = library.plan(list(reversed(shapes)), 70, 6, 2001, 20, world)
+        assert [(it["rank"],) + key(it) for it in again] == [(it["rank"],) + key(it) for it in lpt]
+        assert imb < 1.10 and imb <= imb_s
+        # contiguous blocks of nuclides, first ranks take the remainder
+        owner = {it["nuclide"]: it["rank"] for it in static}
+        assert [owner[s.index] for s in shapes] == sorted(owner[s.index] for s in shapes)
+        for it in lpt:
+            n = shapes[it["nuclide"]].n_el if it["matrix"] == 0 else shapes[it["nuclide"]].n_inel
+            assert it["rows"] == group.tile_bounds(n, it["tile"], it["n_tiles"])[1] - group.tile_bounds(n, it["tile"], it["n_tiles"])[0]
+    assert imb_s > 1.3   # 8 ranks, 24 nuclides: the static blocks are far off
+    lo = [group.tile_bounds(1003, t, 4) for t in range(4)]
     assert lo[0][0] == 0 and lo[-1][1] == 1003 and all(a[1] == b[0] for a, b in zip(lo, lo[1:]))
-
-
-GLOO_LIBRARY = r'''
-import os, sys
-sys.path.insert(0, os.environ["NDPP_ROOT"])
-import numpy as np, torch, torch.distributed as dist
-from ndpp_b200 import library
-dist.init_process_group("gloo")
-rank, world = dist.get_rank(), dist.get_world_size()
-GL = 6
-shapes = [library.NuclideShape(i, 900 + 37 * i, 300 + 11 * i, (0.1 * (i + 1),), 1.5 if i % 2 else None, 1e-11, 20.0)
-          for i in range(5)]
-items = library.make_items(shapes, 4, 3, 101, 5, tile_rows=256)
-plan = library.plan_lpt(items, world)
-grids = {s.index: (np.geomspace(1e-11, 20.003, s.n_el), np.geomspace(0.2, 20.003, s.n_inel + 3)) for s in shapes}
-opened = []
-def open_nuclide(i):
-    opened.append(i); return i
-def integrate(i, it):               # stand-in for the device integration: rows identify (nuclide, E_in)
-    E = grids[i][0 if it.matrix == "el" else 1]
-    lo, hi = library.tile_bounds(len(E), it.tile, it.n_tiles)
-    out = torch.tensor(np.outer(E[lo:hi], np.arange(1, GL + 1)) + 1000.0 * i)
-    out[E[lo:hi] > 20.0] = float("nan")      # the copy rule must fill these from the predecessor
-    return out
-got = library.run_plan(plan[rank], plan, open_nuclide, integrate, lambda h: None, GL, torch.device("cpu"))
-assert len(opened) == len(set(opened)), "a nuclide was opened twice on one rank"
-opened.clear()
-# the in-place form (heights from the host-side grids, one result buffer per rank) assembles the same library
-def rows_of(it):
-    lo, hi = library.tile_bounds(len(grids[it.nuclide][0 if it.matrix == "el" else 1]), it.tile, it.n_tiles)
-    return hi - lo
-def integrate_into(i, it, out):
-    out.copy_(integrate(i, it))
-got2 = library.run_plan(plan[rank], plan, open_nuclide, integrate_into, lambda h: None, GL, torch.device("cpu"),
-                        rows_of=rows_of)
-if rank == 0:
-    assert set(got2) == set(got)
-    for key in got:
-        a = torch.cat([p[2] for p in sorted(got[key], key=lambda p: p[0])])
-        b = torch.cat([p[2] for p in sorted(got2[key], key=lambda p: p[0])])
-        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)), key
-if rank == 0:
-    assert set(got) == {(s.index, m) for s in shapes for m in ("el", "inel")}
-    for (i, m), pieces in got.items():
-        E = grids[i][0 if m == "el" else 1]
-        mat = library.assemble(pieces, E, 20.0).numpy()
-        ref = np.outer(E, np.arange(1, GL + 1)) + 1000.0 * i
-        ref[-1] = ref[-2]
-        assert np.array_equal(mat, ref), (i, m)
-    print("GLOO_LIB_OK")
-dist.destroy_process_group()
-'''
-
-
-def test_library_run_plan_world_size_2_gloo(tmp_path):
-    script = tmp_path / "gloo_lib.py"
-    script.write_text(GLOO_LIBRARY)
-    env = dict(os.environ, NDPP_ROOT=ROOT)
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)], env=env,
-                         capture_output=True, text=True, timeout=240)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "GLOO_LIB_OK" in out.stdout
+    # a nuclide whose inelastic slots have neither a level nor a continuum threshold still plans
+    odd = [library.NuclideShape(0, 500, 200, (), None, 1e-11, 20.0)]
+    it, _ = library.plan(odd, 70, 6, 2001, 20, 2)
+    assert {x["matrix"] for x in it} == {0, 1}
 
 
 def test_fused_closed_forms_are_current_and_bit_identical_on_the_host():

@@ -118,3 +118,34 @@ def freegas_analytic_p0(E, kT, e_bins, A):
             p[g] = integrate.quad(kern, lo, hi, points=[x] if lo < x < hi else None, epsabs=1e-14, epsrel=1e-12,
                                   limit=400)[0] / tot
     return p
+
+
+def check_library_against_oracle(n_check):
+    """`keep` callback of ndpp_b200.library.run_c5: sampled nuclides of a finished library run, assembled on the root
+    device (ndppgpu_library_fetch), against the CPU oracle at 1e-9 rel / 1e-12 abs; the counts go into the report."""
+    def keep(out, run, specs, parsed, e_bins, params):
+        import os
+
+        from ndpp_b200 import synth
+        from oracle import pyoracle
+        rng = np.random.default_rng(5)
+        worst = {"nuclides": [], "cells": 0, "outside_1e-9rel_1e-12abs": 0, "max_abs": 0.0}
+        for i in [s[0] for s in specs][:: max(1, len(specs) // n_check)][:n_check]:
+            nuc, Eel, Einel = parsed[i] if i in parsed else synth.c5_nuclide(specs[i])
+            rn = pyoracle.RefNuclide(nuc, e_bins, params)
+            rn.convert_distro()
+            for m, E in ((0, Eel), (1, Einel)):
+                if E is None or len(E) == 0:
+                    continue
+                mat = run.fetch(i, m, E, e_bins[-1])
+                idx = np.sort(rng.choice(np.nonzero(E <= e_bins[-1])[0], min(24, len(E)), replace=False))
+                ref = rn.elastic(E[idx], n_threads=os.cpu_count()) if m == 0 else \
+                    rn.inelastic(E[idx], n_threads=os.cpu_count())[0]
+                err = np.abs(mat[idx] - ref)
+                worst["cells"] += int(err.size)
+                worst["outside_1e-9rel_1e-12abs"] += int(((err > RTOL * np.abs(ref)) & (err > ATOL)).sum())
+                worst["max_abs"] = max(worst["max_abs"], float(err.max()))
+            worst["nuclides"].append(int(i))
+            rn.close()
+        out["parity_vs_oracle"] = worst
+    return keep
