@@ -126,7 +126,9 @@ public:
         if (ndppgpu_abi_version() != NDPPGPU_ABI_VERSION) fatal_error("libndppgpu.so: ABI version mismatch");
         if (ndppgpu_init(device, &h_) != 0) fatal_error(last_error(nullptr));
     }
-    ~Context() { if (h_) ndppgpu_finalize(h_); }
+    // a context that belongs to a device group (ndppgpu_group_ctx): used, not owned
+    Context(void* borrowed, bool) : h_(borrowed), owned_(false) {}
+    ~Context() { if (h_ && owned_) ndppgpu_finalize(h_); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     void* handle() const { return h_; }
@@ -147,6 +149,38 @@ public:
 
 private:
     void* h_ = nullptr;
+    bool owned_ = true;
+};
+
+// ---- several GPUs: the devices of this process working on one nuclide / one library (ndppgpu_group_*) -------------
+// Replaces what the reference spreads over MPI ranks in its own driver (partition_work, src/ndpp.F90:934-950).
+class DeviceGroup {
+public:
+    explicit DeviceGroup(int n_devices = 0)   // 0: every GPU of the box
+    {
+        if (ndppgpu_abi_version() != NDPPGPU_ABI_VERSION) fatal_error("libndppgpu.so: ABI version mismatch");
+        if (ndppgpu_group_init(n_devices, nullptr, &g_) != 0) fatal_error(Context::last_error(nullptr));
+        ndppgpu_group_info(g_, &world_, &n_local_, nullptr);
+        root_.reset(new Context(ndppgpu_group_ctx(g_, 0), false));
+    }
+    ~DeviceGroup() { root_.reset(); if (g_) ndppgpu_group_finalize(g_); }
+    DeviceGroup(const DeviceGroup&) = delete;
+    DeviceGroup& operator=(const DeviceGroup&) = delete;
+    void* handle() const { return g_; }
+    int world() const { return world_; }
+    const Context& root() const { return *root_; }       // context of the root device: receives the assembled matrices
+    void check(int rc) const { root_->check(rc); }
+    ndppgpu_stats_t stats(int local_index) const
+    {
+        ndppgpu_stats_t s;
+        check(ndppgpu_stats(ndppgpu_group_ctx(g_, local_index), &s, 0));
+        return s;
+    }
+
+private:
+    void* g_ = nullptr;
+    int world_ = 1, n_local_ = 1;
+    std::unique_ptr<Context> root_;
 };
 
 namespace detail {
@@ -161,6 +195,24 @@ public:
                  int order, int mu_bins, bool nuscatt, const Settings& st = Settings())
         : ctx_(ctx)
     {
+        init(nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
+    }
+    // the same set replicated on every device of a group; calc_*_grid then shard the E_in grid over the devices and
+    // gather the columns to the root (ndppgpu_group_*): same arguments, same results
+    ScattDataSet(const DeviceGroup& group, const Nuclide& nuc, const std::vector<double>& energy_bins, int scatt_type,
+                 int order, int mu_bins, bool nuscatt, const Settings& st = Settings())
+        : ctx_(group.root()), group_(group.handle())
+    {
+        init(nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
+    }
+    ~ScattDataSet() { clear(); }
+    ScattDataSet(const ScattDataSet&) = delete;
+    ScattDataSet& operator=(const ScattDataSet&) = delete;
+
+private:
+    void init(const Nuclide& nuc, const std::vector<double>& energy_bins, int scatt_type, int order, int mu_bins,
+              bool nuscatt, const Settings& st)
+    {
         if (energy_bins.size() < 2) fatal_error("calc_scatt: energy_bins needs at least two edges");
         groups_ = (int)energy_bins.size() - 1;
         order_ = (scatt_type == SCATT_TYPE_LEGENDRE) ? order + 1 : order;  // src/scattdata_header.F90:114-118
@@ -171,9 +223,14 @@ public:
         p.sab_threshold = st.sab_threshold; p.brent_mu_thresh = st.brent_mu_thresh;
         p.adaptive_mu_tol = st.adaptive_mu_tol; p.adaptive_eout_tol = st.adaptive_eout_tol;
         if (nuc.energy.size() != nuc.elastic.size()) fatal_error("calc_scatt: nuc % energy and nuc % elastic differ in size");
-        ctx_.check(ndppgpu_nuclide_create(ctx_.handle(), nuc.awr, nuc.kT, nuc.freegas_cutoff, (int)nuc.energy.size(),
-                                          nuc.energy.data(), nuc.elastic.data(), energy_bins.data(),
-                                          (int)energy_bins.size(), &p, &h_));
+        if (group_)
+            ctx_.check(ndppgpu_group_nuclide_create(group_, nuc.awr, nuc.kT, nuc.freegas_cutoff, (int)nuc.energy.size(),
+                                                    nuc.energy.data(), nuc.elastic.data(), energy_bins.data(),
+                                                    (int)energy_bins.size(), &p, &h_));
+        else
+            ctx_.check(ndppgpu_nuclide_create(ctx_.handle(), nuc.awr, nuc.kT, nuc.freegas_cutoff, (int)nuc.energy.size(),
+                                              nuc.energy.data(), nuc.elastic.data(), energy_bins.data(),
+                                              (int)energy_bins.size(), &p, &h_));
         try {
             for (size_t i = 0; i < nuc.reactions.size(); ++i) {
                 const Reaction& rxn = nuc.reactions[i];
@@ -183,16 +240,14 @@ public:
                     ed = ed ? ed->next.get() : nullptr;
                 } while (ed != nullptr);
             }
-            ctx_.check(ndppgpu_convert_distro(h_));
+            ctx_.check(group_ ? ndppgpu_group_convert_distro(h_) : ndppgpu_convert_distro(h_));
         } catch (...) {
             clear();
             throw;
         }
     }
-    ~ScattDataSet() { clear(); }
-    ScattDataSet(const ScattDataSet&) = delete;
-    ScattDataSet& operator=(const ScattDataSet&) = delete;
 
+public:
     int order() const { return order_; }    // L
     int groups() const { return groups_; }  // G
 
@@ -200,7 +255,8 @@ public:
     void calc_elastic_grid(const std::vector<double>& Ein, std::vector<double>& el_mat) const
     {
         el_mat.assign(Ein.size() * (size_t)groups_ * order_, 0.0);
-        ctx_.check(ndppgpu_elastic(h_, Ein.data(), (int)Ein.size(), el_mat.data()));
+        ctx_.check(group_ ? ndppgpu_group_elastic(h_, Ein.data(), (int)Ein.size(), el_mat.data())
+                          : ndppgpu_elastic(h_, Ein.data(), (int)Ein.size(), el_mat.data()));
     }
     // calc_inelastic_grid (src/scatt.F90:682-778); nuinel_mat stays empty unless nuscatt
     void calc_inelastic_grid(const std::vector<double>& Ein, bool nuscatt, std::vector<double>& inel_mat,
@@ -208,8 +264,10 @@ public:
     {
         inel_mat.assign(Ein.size() * (size_t)groups_ * order_, 0.0);
         if (nuscatt) nuinel_mat.assign(inel_mat.size(), 0.0); else nuinel_mat.clear();
-        ctx_.check(ndppgpu_inelastic(h_, Ein.data(), (int)Ein.size(), inel_mat.data(),
-                                     nuscatt ? nuinel_mat.data() : nullptr));
+        ctx_.check(group_ ? ndppgpu_group_inelastic(h_, Ein.data(), (int)Ein.size(), inel_mat.data(),
+                                                    nuscatt ? nuinel_mat.data() : nullptr)
+                          : ndppgpu_inelastic(h_, Ein.data(), (int)Ein.size(), inel_mat.data(),
+                                              nuscatt ? nuinel_mat.data() : nullptr));
     }
     // calc_*_grid + apply_tol_scatt + thin_grid with only the kept columns copied back (src/ndpp.F90:607-648);
     // Ein and the matrices are cut to the points kept, as thin_grid re-allocates them
@@ -218,6 +276,11 @@ public:
                               double& max_abs_err) const
     {
         const size_t w = (size_t)groups_ * order_;
+        if (group_) {   // integrate on the group, then the two steps of src/ndpp.F90:611-648 on the root device
+            calc_elastic_grid(Ein, el_mat);
+            post(Ein, print_tol, thin_tol, tokeep, el_mat, nullptr, compression, max_abs_err);
+            return;
+        }
         el_mat.assign(Ein.size() * w, 0.0);
         int kept = 0;
         ctx_.check(ndppgpu_elastic_thinned(h_, Ein.data(), (int)Ein.size(), print_tol, thin_tol, tokeep.data(),
@@ -230,6 +293,11 @@ public:
                                 std::vector<double>& nuinel_mat, double& compression, double& max_abs_err) const
     {
         const size_t w = (size_t)groups_ * order_;
+        if (group_) {
+            calc_inelastic_grid(Ein, nuscatt, inel_mat, nuinel_mat);
+            post(Ein, print_tol, thin_tol, tokeep, inel_mat, nuscatt ? &nuinel_mat : nullptr, compression, max_abs_err);
+            return;
+        }
         inel_mat.assign(Ein.size() * w, 0.0);
         if (nuscatt) nuinel_mat.assign(inel_mat.size(), 0.0); else nuinel_mat.clear();
         int kept = 0;
@@ -243,11 +311,30 @@ public:
     // rxn_data(i) % clear() (src/scatt.F90:153-155)
     void clear()
     {
-        if (h_) ndppgpu_nuclide_free(h_);
+        if (h_) { if (group_) ndppgpu_group_nuclide_free(h_); else ndppgpu_nuclide_free(h_); }
         h_ = nullptr;
     }
 
 private:
+    // apply_tol_scatt and thin_grid of an assembled matrix set, on the root device
+    void post(std::vector<double>& Ein, double print_tol, double thin_tol, const std::vector<double>& tokeep,
+              std::vector<double>& mat, std::vector<double>* nu, double& compression, double& max_abs_err) const
+    {
+        const int NE = (int)Ein.size();
+        compression = 0.0; max_abs_err = 0.0;
+        if (NE == 0) return;
+        ctx_.check(ndppgpu_apply_tol(ctx_.handle(), mat.data(), NE, groups_, order_, print_tol));
+        if (nu) ctx_.check(ndppgpu_apply_tol(ctx_.handle(), nu->data(), NE, groups_, order_, print_tol));
+        if (thin_tol > 0.0) {
+            int kept = 0;
+            ctx_.check(ndppgpu_thin_grid(ctx_.handle(), Ein.data(), mat.data(), nu ? nu->data() : nullptr, NE,
+                                         groups_ * order_, tokeep.data(), (int)tokeep.size(), thin_tol, &kept, &compression,
+                                         &max_abs_err));
+            Ein.resize(kept);
+            mat.resize((size_t)kept * groups_ * order_);
+            if (nu) nu->resize((size_t)kept * groups_ * order_);
+        }
+    }
     void add_slot(int i_rxn, const Reaction& rxn, const DistEnergy* ed)
     {
         std::vector<double> yl, pv;
@@ -257,7 +344,7 @@ private:
         const bool ha = rxn.has_angle_dist;
         if (ha && (ad.type.size() != ad.energy.size() || ad.location.size() != ad.energy.size()))
             fatal_error("calc_scatt: inconsistent angular-distribution arrays");
-        ctx_.check(ndppgpu_nuclide_add_reaction(
+        ctx_.check((group_ ? ndppgpu_group_nuclide_add_reaction : ndppgpu_nuclide_add_reaction)(
             h_, i_rxn, rxn.MT, rxn.Q_value, rxn.threshold, rxn.scatter_in_cm ? 1 : 0, ha ? 1 : 0, ed ? 1 : 0,
             ed ? ed->law : 0, rxn.multiplicity, detail::ptr_or_null(yl), (int)yl.size(), detail::ptr_or_null(rxn.sigma),
             (int)rxn.sigma.size(), detail::ptr_or_null(pv), (int)pv.size(), ha ? detail::ptr_or_null(ad.energy) : nullptr,
@@ -266,6 +353,7 @@ private:
             ed ? detail::ptr_or_null(ed->data) : nullptr, ed ? (int)ed->data.size() : 0));
     }
     const Context& ctx_;
+    void* group_ = nullptr;   // ndppgpu group handle when the set lives on a device group
     void* h_ = nullptr;
     int order_ = 0, groups_ = 0;
 };
@@ -280,6 +368,20 @@ inline void calc_scatt(const Context& ctx, const Nuclide& nuc, const std::vector
                        std::vector<double>& nuinel_mat, const Settings& st = Settings())
 {
     ScattDataSet rxn_data(ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
+    rxn_data.calc_elastic_grid(Ein_el, el_mat);
+    inel_mat.clear();
+    nuinel_mat.clear();
+    if (!Ein_inel.empty()) rxn_data.calc_inelastic_grid(Ein_inel, nuscatt, inel_mat, nuinel_mat);
+    rxn_data.clear();
+}
+
+// calc_scatt on a device group: the single-process, several-GPU form of the same call
+inline void calc_scatt(const DeviceGroup& group, const Nuclide& nuc, const std::vector<double>& energy_bins, int scatt_type,
+                       int& order, int mu_bins, bool nuscatt, const std::vector<double>& Ein_el,
+                       const std::vector<double>& Ein_inel, std::vector<double>& el_mat, std::vector<double>& inel_mat,
+                       std::vector<double>& nuinel_mat, const Settings& st = Settings())
+{
+    ScattDataSet rxn_data(group, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
     rxn_data.calc_elastic_grid(Ein_el, el_mat);
     inel_mat.clear();
     nuinel_mat.clear();

@@ -318,7 +318,8 @@ typedef struct {
     int items, opens;                        /* items of the plan; nuclides opened by the local devices */
     double device_s_max;                     /* CUDA-event time from a device's first upload to the end of its part of the
                                                 gather, slowest local device */
-    double reserved[3];
+    double alloc_s_max;                      /* host time a local device spent allocating its result buffer */
+    double reserved[2];
 } ndppgpu_library_report;
 int ndppgpu_library_create(void *group, int G, int L, int nuscatter, const ndppgpu_item *items, int n_items, void **lib);
 int ndppgpu_library_run(void *lib, ndppgpu_open_fn open, ndppgpu_close_fn close, void *user, ndppgpu_library_report *rep);

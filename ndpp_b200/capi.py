@@ -71,7 +71,7 @@ class LibraryReportC(C.Structure):
     _fields_ = [("wall_s", C.c_double), ("compute_s", C.c_double), ("gather_s", C.c_double), ("open_s_max", C.c_double),
                 ("integrate_s_max", C.c_double), ("kernel_s_max", C.c_double), ("kernel_s_sum", C.c_double),
                 ("moment_evals", C.c_longlong), ("items", C.c_int), ("opens", C.c_int), ("device_s_max", C.c_double),
-                ("reserved", C.c_double * 3)]
+                ("alloc_s_max", C.c_double), ("reserved", C.c_double * 2)]
 
 
 OPEN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_double)),

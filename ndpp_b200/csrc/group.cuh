@@ -818,7 +818,7 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
     const int W = g->world;
     b->flat.clear(); b->flat.resize(g->n_local);
     b->flat_nu.clear(); b->flat_nu.resize(g->n_local);
-    std::vector<double> t_open(g->n_local, 0.0), t_int(g->n_local, 0.0), t_gather(g->n_local, 0.0), k_ms(g->n_local, 0.0);
+    std::vector<double> t_open(g->n_local, 0.0), t_int(g->n_local, 0.0), t_alloc(g->n_local, 0.0), k_ms(g->n_local, 0.0);
     std::vector<int> opens(g->n_local, 0);
     std::vector<cudaEvent_t> ev0(g->n_local, nullptr), ev1(g->n_local, nullptr);   // device-side clock of the whole run
     std::vector<double> dev_ms(g->n_local, 0.0);
@@ -834,8 +834,19 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
         CK(c, cudaEventCreate(&ev0[li]));
         CK(c, cudaEventCreate(&ev1[li]));
         CK(c, cudaEventRecord(ev0[li], c->stream));
-        if (dev_alloc(c, b->flat[li], std::max<size_t>(b->rows_of_rank[r], 1) * GL * sizeof(double))) return 1;
-        if (b->nuscatter && dev_alloc(c, b->flat_nu[li], std::max<size_t>(b->rows_of_rank[r], 1) * GL * sizeof(double))) return 1;
+        const auto t_a = std::chrono::steady_clock::now();
+        double *flat = nullptr, *flat_nu = nullptr;
+        if (r == 0) {   // the root integrates in place into the buffer the other devices' results are gathered into
+            const size_t tot = std::max<size_t>(b->part_off[W], 1);
+            if (dev_alloc(c, b->parts, tot * GL * sizeof(double))) return 1;
+            if (b->nuscatter && dev_alloc(c, b->parts_nu, tot * GL * sizeof(double))) return 1;
+            flat = b->parts.as<double>(); flat_nu = b->parts_nu.as<double>();
+        } else {
+            if (dev_alloc(c, b->flat[li], std::max<size_t>(b->rows_of_rank[r], 1) * GL * sizeof(double))) return 1;
+            if (b->nuscatter && dev_alloc(c, b->flat_nu[li], std::max<size_t>(b->rows_of_rank[r], 1) * GL * sizeof(double))) return 1;
+            flat = b->flat[li].as<double>(); flat_nu = b->flat_nu[li].as<double>();
+        }
+        t_alloc[li] = secs(t_a);
         void* nuc = nullptr;
         int cur = -1;
         const double *Ein_el = nullptr, *Ein_inel = nullptr;
@@ -868,11 +879,11 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
                                " rows, the plan says " + std::to_string(pc.rows);
                 return 1;
             }
-            double* out = b->flat[li].as<double>() + pc.off_rows * GL;
+            double* out = flat + pc.off_rows * GL;
             int e = 0;
             if (pc.matrix == 0) e = elastic_dev((Nuclide*)nuc, d_Eel.as<double>() + lo, hi - lo, out);
             else e = inelastic_dev((Nuclide*)nuc, d_Einel.as<double>() + lo, hi - lo, out,
-                                   b->nuscatter ? b->flat_nu[li].as<double>() + pc.off_rows * GL : nullptr);
+                                   b->nuscatter ? flat_nu + pc.off_rows * GL : nullptr);
             if (e) { shut(); return 1; }
             t_int[li] += secs(t0);
         }
@@ -887,14 +898,6 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
     const double t_compute = secs(t_all);
     // one gather: every device's buffer to the root
     const auto t_g = std::chrono::steady_clock::now();
-    if (g->first == 0) {
-        Ctx* c = g->ctx[0];
-        CK(c, cudaSetDevice(c->device));
-        const size_t tot = std::max<size_t>(b->part_off[W], 1);
-        if (dev_alloc(c, b->parts, tot * GL * sizeof(double))) return 1;
-        if (b->nuscatter && dev_alloc(c, b->parts_nu, tot * GL * sizeof(double))) return 1;
-        CK(c, cudaStreamSynchronize(c->stream));
-    }
     rc = group_parallel(g, [&](int li) -> int {
         Ctx* c = g->ctx[li];
         const int r = g->first + li;
@@ -911,10 +914,6 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
                     g->gathered_bytes += (long long)(nq * sizeof(double) * (b->nuscatter ? 2 : 1));
                 }
                 NCK(g, g_nccl.GroupEnd());
-            }
-            if (n) {
-                CK(c, cudaMemcpyAsync(b->parts.p, b->flat[li].p, n * sizeof(double), cudaMemcpyDeviceToDevice, cs));
-                if (b->nuscatter) CK(c, cudaMemcpyAsync(b->parts_nu.p, b->flat_nu[li].p, n * sizeof(double), cudaMemcpyDeviceToDevice, cs));
             }
         } else if (n) {
             NCK(g, g_nccl.GroupStart());
@@ -954,6 +953,7 @@ int ndppgpu_library_run(void* lib, ndppgpu_open_fn open, ndppgpu_close_fn close,
         R.kernel_s_max = std::max(R.kernel_s_max, k_ms[li] * 1e-3);
         R.kernel_s_sum += k_ms[li] * 1e-3;
         R.device_s_max = std::max(R.device_s_max, dev_ms[li] * 1e-3);
+        R.alloc_s_max = std::max(R.alloc_s_max, t_alloc[li]);
     }
     R.items = (int)b->items.size();
     for (auto& pc : b->pieces) R.moment_evals += (long long)pc.rows * (long long)GL * (pc.matrix == 1 && b->nuscatter ? 2 : 1);

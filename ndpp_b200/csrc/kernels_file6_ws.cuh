@@ -15,8 +15,12 @@
 //             order (:1246-1252).  A single warp of segment integrals fills 89 % of the FP64 pipe
 //             (scratch/cbench.cu), so the pipe stays busy while the producers wait on memory.
 //
-// Consumers take (E_in, group) tasks from a global counter (persistent grid) and post them to their
-// producers, so there is no block-level barrier and no tail imbalance inside a block.
+// Consumers take (E_in, group, outgoing energy) tasks from a global counter (persistent grid) and post them to
+// their producers, so there is no block-level barrier and no tail imbalance inside a block.  A task is one of the
+// NE_PER_GRP outgoing energies of an (E_in, group) pair (65 windows, ~0.1 ms of a warp pair): with whole pairs as
+// tasks (20 x larger) the last wave of a launch left the device a third empty on a nuclide sharded over 8 GPUs
+// (16 800 pairs for 1 776 consumer warps).  The moments of a task go to `part`; k_file6_reduce adds them over the
+// outgoing energies in the reference's order with the trapezoid weights (:1246-1252), so the bits do not change.
 //
 // The arithmetic is the one of k_file6_cm, operation for operation (results are bit-identical; the
 // GPU tests compare the two kernels).  What differs is bookkeeping:
@@ -155,6 +159,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #ifndef F6_NPROD
 #define F6_NPROD 1
 #endif
+#ifndef F6_CHUNK
+#define F6_CHUNK 4         // outgoing energies per task; C2 on one B200, kernel ms: 1 -> 162.3, 4 -> 159.1, 20 (whole pair) -> 160.1
+                           // (same box); on an eighth of the nuclide (8 GPUs) whole pairs left a 6 % tail
+#endif
+#ifndef F6_SHFL_POWERS
+#define F6_SHFL_POWERS 1   // a segment's xhigh powers come from the next lane by shuffle: 159.1 -> 156.4 ms (0: recomputed)
+#endif
 #ifndef F6_STAGE_BITS
 #define F6_STAGE_BITS 3   // ring of 2^bits windows per producer; A/B on C2 at 3 blocks/SM (same box, +-0.3 ms): 4 stages 161.0 ms, 8: 160.3, 16: 161.8
 #endif
@@ -185,7 +196,6 @@ struct F6Shared {
     unsigned long long task_full[F6_CONS][2];   // consumer -> its producers: next (E_in, group) task
     unsigned long long task_empty[F6_CONS][2];
     long long task[F6_CONS][2];
-    double d[F6_CONS][NDPP_MAX_L];  // trapezoid accumulators of the consumers (warp-uniform)
 };
 
 // Scalars of one (E_in, group) pair (:1138-1173), computed identically by both roles.
@@ -315,13 +325,23 @@ __device__ __forceinline__ double f6_point(const F6PointCtx& C, double Eo, doubl
     return proby * J * pEo;
 }
 
-// tasks t = b * G + g, b = 0 .. na-1 over the batch's active E_in act[a0 + b]
+// Eo of outgoing energy `it`, accumulated as the reference accumulates it (:1169-1173)
+__device__ __forceinline__ double f6_item_energy(const F6Pair& P, int it)
+{
+    double Eo = P.Eb_lo - P.dEo;
+    for (int i = 0; i <= it; ++i) Eo = Eo + P.dEo;
+    return Eo;
+}
+
+// tasks t = (b * G + g) * nCh + chunk, b = 0 .. na-1 over the batch's active E_in act[a0 + b]; a task covers F6_CHUNK
+// consecutive outgoing energies; part[((b * G + g) * K + it) * L + l] receives the integral over mu of outgoing energy
+// `it` (zero-filled by the caller: inactive and skipped energies write nothing)
 template <int LT>
 __global__ void __launch_bounds__(F6_THREADS, F6_BLOCKS_PER_SM)
 k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec* __restrict__ rec,
               const int* __restrict__ sorted, const double* __restrict__ femu, const double* __restrict__ rmu,
               const int* __restrict__ act, int a0, int na, unsigned long long* __restrict__ counter,
-              double* __restrict__ raw)
+              double* __restrict__ part)
 {
     __shared__ F6Shared sh;
     constexpr int L = LT;
@@ -343,7 +363,8 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    const long long n_tasks = (long long)na * G;
+    const int nCh = (K + F6_CHUNK - 1) / F6_CHUNK;   // tasks per (E_in, group) pair
+    const long long n_tasks = (long long)na * G * nCh;
     const int nW = (M - 1 + 30) / 31;  // windows per outgoing energy
     const uint32_t tfull0 = smem_u32(&sh.task_full[cons][0]), tempty0 = smem_u32(&sh.task_empty[cons][0]);
     int tslot = 0;
@@ -361,6 +382,7 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
         F6PointCtx C;
         C.mu = nuc.mu; C.rmu = rmu; C.M = M;
         C.div_dmu.set(nuc.mu[1] - nuc.mu[0]);
+        int cur_b = -1;
         for (;;) {
             mbar_wait(tfull0 + 8u * tslot, tphase);
             const long long t = sh.task[cons][tslot];
@@ -370,23 +392,25 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
             if (t < 0) break;
 
             F6Pair P;
-            f6_pair_setup(nuc, Ein, ub, act, a0, t, P);
+            f6_pair_setup(nuc, Ein, ub, act, a0, t / nCh, P);
             if (!P.active) continue;
-            C.R = rec + (size_t)P.b * ub.maxU;
-            C.fE = femu + (size_t)P.b * ub.maxU * M;
-            C.NPu = P.NPu;
-            C.use_guess = sorted[P.b] != 0;
-            C.eo0 = __ldg(&C.R[0].eo); C.eoLast = __ldg(&C.R[P.NPu - 1].eo);
-
-            double Eo = P.Eb_lo - P.dEo;
+            const int it0 = (int)(t % nCh) * F6_CHUNK, it1 = min(K, it0 + F6_CHUNK);
+            double Eo = f6_item_energy(P, it0 - 1);
+            if (P.b != cur_b) {   // consecutive tasks mostly share their E_in
+                cur_b = P.b;
+                C.R = rec + (size_t)P.b * ub.maxU;
+                C.fE = femu + (size_t)P.b * ub.maxU * M;
+                C.NPu = P.NPu;
+                C.use_guess = sorted[P.b] != 0;
+                C.eo0 = __ldg(&C.R[0].eo); C.eoLast = __ldg(&C.R[P.NPu - 1].eo);
+            }
             int w0 = 0;  // windows of the task before this outgoing energy, modulo F6_NPROD
-            for (int it = 0; it < K; ++it) {
-                Eo = Eo + P.dEo;  // accumulated as the reference accumulates it (:1169-1173)
+            for (int it = it0; it < it1; ++it) {
+                Eo = Eo + P.dEo;
                 F6Item I;
                 f6_item_setup(P, Eo, M, I);
                 if (I.skip) continue;
-                // this producer's windows: j with (w0 + j) % F6_NPROD == q
-                int j = q - w0;
+                int j = q - w0;   // this producer's windows: j with (w0 + j) % F6_NPROD == q
                 if (j < 0) j += F6_NPROD;
                 w0 = (w0 + nW) % F6_NPROD;
                 int guess = -1;
@@ -410,36 +434,44 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
         uint32_t pos = 0;
         const uint32_t full00 = smem_u32(&sh.full[cons][0][0]), empty00 = smem_u32(&sh.empty[cons][0][0]);
         const uint32_t buf00 = smem_u32(&sh.buf[cons][0][0][0]);
-        for (;;) {
-            long long t = 0;
-            if (lane == 0) t = (long long)atomicAdd(counter, 1ULL);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= n_tasks) t = -1;
-            // hand the task to the producers
+        // Tasks are taken one ahead: the next task is fetched and posted to the producers' two-slot mailbox before the
+        // current one is consumed, so the producers run on into the next task's windows while the consumer finishes
+        // this one (no pipeline bubble at a task boundary: the counter's round trip and the producers' set-up are hidden).
+        auto fetch = [&]() -> long long {
+            long long v = 0;
+            if (lane == 0) v = (long long)atomicAdd(counter, 1ULL);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            return v >= n_tasks ? -1 : v;
+        };
+        auto post = [&](long long v) {
             mbar_wait(tempty0 + 8u * tslot, tphase ^ 1u);
             if (lane == 0) {
-                sh.task[cons][tslot] = t;
+                sh.task[cons][tslot] = v;
                 mbar_arrive(tfull0 + 8u * tslot);
             }
             F6_TASK_ADVANCE();
-            if (t < 0) break;
+        };
+        long long t = fetch();
+        post(t);
+        for (long long t_next = 0; t >= 0; t = t_next) {
+            t_next = fetch();
+            post(t_next);
 
             F6Pair P;
-            f6_pair_setup(nuc, Ein, ub, act, a0, t, P);
+            f6_pair_setup(nuc, Ein, ub, act, a0, t / nCh, P);
             if (!P.active) continue;
-            double* const d = sh.d[cons];
-            if (lane < NDPP_MAX_L) d[lane] = 0.0;
-            __syncwarp();
-            double Eo = P.Eb_lo - P.dEo;
+            const int it0 = (int)(t % nCh) * F6_CHUNK, it1 = min(K, it0 + F6_CHUNK);
+            double Eo = f6_item_energy(P, it0 - 1);
             int wq = 0;
-            for (int it = 0; it < K; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 Eo = Eo + P.dEo;
                 F6Item I;
                 f6_item_setup(P, Eo, M, I);
+                if (I.skip) continue;
                 double fEl[NDPP_MAX_L];
 #pragma unroll
                 for (int l = 0; l < NDPP_MAX_L; ++l) fEl[l] = 0.0;
-                if (!I.skip) {
+                {
                     double pd = (double)lane;   // (double)(base + lane), advanced by the exact 31.0 per window
                     for (int base = 0; base < M - 1; base += 31, pd += 31.0) {
                         const int p = base + lane;
@@ -455,7 +487,24 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
                         pos = (pos & ~(PM << (PB * wq))) | (((sp + 1u) & PM) << (PB * wq));  // stage++, phase flips on wrap
                         if (++wq == F6_NPROD) wq = 0;
                         // a segment whose two end values are zero adds exact zeros: skipped
-                        if (lane < 31 && p + 1 < M && (fv != 0.0 || fnext != 0.0)) {
+                        const bool mine = lane < 31 && p + 1 < M && (fv != 0.0 || fnext != 0.0);
+#if F6_SHFL_POWERS
+                        // The right end of a lane's segment is the left end of the next lane's: x = mu_l_min + dmu * pd
+                        // with pd an exact integer, so the powers of xhigh are bitwise the next lane's powers of xlow.
+                        // Each point's powers are computed once and handed down by shuffles (off the FP64 pipe).
+                        if (__any_sync(0xffffffffu, mine)) {
+                            const double x = I.mu_l_min + I.dmu * pd;
+                            Powers A, B;
+                            make_powers(x, A);
+                            const double xh = __shfl_down_sync(0xffffffffu, x, 1);
+#define F6_DOWN(k) if constexpr (LT + 1 >= k) B.p##k = __shfl_down_sync(0xffffffffu, A.p##k, 1); else B.p##k = 0.0;
+                            F6_DOWN(2) F6_DOWN(3) F6_DOWN(4) F6_DOWN(5) F6_DOWN(6) F6_DOWN(7) F6_DOWN(8) F6_DOWN(9) F6_DOWN(10)
+                            F6_DOWN(11) F6_DOWN(12)
+#undef F6_DOWN
+                            if (mine) add_int_pn_tablelin<LT>(L, x, xh, fv, fnext, A, B, fEl);
+                        }
+#else
+                        if (mine) {
                             const double x = I.mu_l_min + I.dmu * pd;
                             const double xh = I.mu_l_min + I.dmu * (pd + 1.0);
                             Powers A, B;
@@ -463,100 +512,40 @@ k_file6_cm_ws(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec*
                             make_powers(xh, B);
                             add_int_pn_tablelin<LT>(L, x, xh, fv, fnext, A, B, fEl);
                         }
+#endif
                     }
                 }
-                // trapezoid over the outgoing energies, in the reference's order (:1246-1252)
+                // the integral over mu of this outgoing energy; k_file6_reduce applies the trapezoid over the energies
 #pragma unroll
                 for (int l = 0; l < NDPP_MAX_L; ++l) {
                     if (l < L) {
                         const double v = warp_sum(fEl[l]);
-                        if (lane == 0) d[l] = (it != 0 && it != K - 1) ? d[l] + 2.0 * v : d[l] + v;
+                        if (lane == 0) part[((size_t)(t / nCh) * K + it) * L + l] = v;
                     }
                 }
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int l = 0; l < NDPP_MAX_L; ++l)
-                    if (l < L) raw[((size_t)P.iEin * G + P.g) * L + l] = d[l] * P.dEo * 0.5;
             }
         }
     }
 #undef F6_TASK_ADVANCE
 }
 
-// The same work with one role per warp (no pipeline): every warp takes (E_in, group) tasks itself and
-// alternates point evaluation and segment integrals.  Kept for the A/B measurement in DESIGN.md.
-template <int LT>
-__global__ void __launch_bounds__(128, 4)
-k_file6_cm_solo(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const UbRec* __restrict__ rec,
-                const int* __restrict__ sorted, const double* __restrict__ femu, const double* __restrict__ rmu,
-                const int* __restrict__ act, int a0, int na, unsigned long long* __restrict__ counter,
-                double* __restrict__ raw)
+// Trapezoid over the NE_PER_GRP outgoing energies of every (E_in, group) pair of the batch, in the reference's order
+// with its weights 1, 2, ..., 2, 1 and the final * dEo * 0.5 (:1246-1252).  One thread per (pair, order).
+__global__ void k_file6_reduce(NucDev nuc, const double* __restrict__ Ein, UbDev ub, const int* __restrict__ act, int a0,
+                               int na, int L, const double* __restrict__ part, double* __restrict__ raw)
 {
-    __shared__ double dsh[4][NDPP_MAX_L];
-    constexpr int L = LT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int M = nuc.M, K = nuc.ne_per_grp, G = nuc.G;
-    const long long n_tasks = (long long)na * G;
-    F6PointCtx C;
-    C.mu = nuc.mu; C.rmu = rmu; C.M = M;
-    C.div_dmu.set(nuc.mu[1] - nuc.mu[0]);
-    double* const d = dsh[warp];
-    for (;;) {
-        long long t = 0;
-        if (lane == 0) t = (long long)atomicAdd(counter, 1ULL);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tasks) break;
-        F6Pair P;
-        f6_pair_setup(nuc, Ein, ub, act, a0, t, P);
-        if (!P.active) continue;
-        C.R = rec + (size_t)P.b * ub.maxU;
-        C.fE = femu + (size_t)P.b * ub.maxU * M;
-        C.NPu = P.NPu;
-        C.use_guess = sorted[P.b] != 0;
-        C.eo0 = __ldg(&C.R[0].eo); C.eoLast = __ldg(&C.R[P.NPu - 1].eo);
-        if (lane < NDPP_MAX_L) d[lane] = 0.0;
-        __syncwarp();
-        double Eo = P.Eb_lo - P.dEo;
-        for (int it = 0; it < K; ++it) {
-            Eo = Eo + P.dEo;
-            F6Item I;
-            f6_item_setup(P, Eo, M, I);
-            double fEl[NDPP_MAX_L];
-#pragma unroll
-            for (int l = 0; l < NDPP_MAX_L; ++l) fEl[l] = 0.0;
-            if (!I.skip) {
-                int guess = -1;
-                for (int base = 0; base < M - 1; base += 31) {
-                    const int p = base + lane;
-                    const double x = I.mu_l_min + I.dmu * (double)p;
-                    double fv = 0.0;
-                    if (p < M) fv = f6_point(C, Eo, I.c, x, guess);
-                    const double fnext = __shfl_down_sync(0xffffffffu, fv, 1);
-                    if (lane < 31 && p + 1 < M && (fv != 0.0 || fnext != 0.0)) {
-                        const double xh = I.mu_l_min + I.dmu * (double)(p + 1);
-                        Powers A, B;
-                        make_powers(x, A);
-                        make_powers(xh, B);
-                        add_int_pn_tablelin<LT>(L, x, xh, fv, fnext, A, B, fEl);
-                    }
-                }
-            }
-#pragma unroll
-            for (int l = 0; l < NDPP_MAX_L; ++l) {
-                if (l < L) {
-                    const double v = warp_sum(fEl[l]);
-                    if (lane == 0) d[l] = (it != 0 && it != K - 1) ? d[l] + 2.0 * v : d[l] + v;
-                }
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int l = 0; l < NDPP_MAX_L; ++l)
-                if (l < L) raw[((size_t)P.iEin * G + P.g) * L + l] = d[l] * P.dEo * 0.5;
-        }
-        __syncwarp();
-    }
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int G = nuc.G, K = nuc.ne_per_grp;
+    if (id >= (long long)na * G * L) return;
+    const long long pair = id / L;
+    const int l = (int)(id % L);
+    F6Pair P;
+    f6_pair_setup(nuc, Ein, ub, act, a0, pair, P);
+    if (!P.active) return;   // raw was zero-filled
+    const double* __restrict__ v = part + (size_t)pair * K * L + l;
+    double d = 0.0;
+    for (int it = 0; it < K; ++it) d = (it != 0 && it != K - 1) ? d + 2.0 * v[(size_t)it * L] : d + v[(size_t)it * L];
+    raw[((size_t)P.iEin * G + P.g) * L + l] = d * P.dEo * 0.5;
 }
 
 }  // namespace ndpp

@@ -44,13 +44,12 @@ struct Ctx {
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
     int fg_split_depth = 2;  // NDPPGPU_FG_SPLIT: levels of the outer recursion one work item walks (1..4); C3: 506 / 485 / 455 / 452 ms at 4 / 3 / 2 / 1
     long long fg_queue_cap = 0;               // NDPPGPU_FG_QUEUE: first-attempt capacity of the item queue (tests)
-    bool f6_solo = false;    // NDPPGPU_F6_SOLO=1: one role per warp on the same tables (A/B measurement)
     bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
     // file-6 CM scratch (records, sorted flags, materialised unit-base tables): kept for the life of the context
     // and grown on demand.  cudaMemGetInfo plus a multi-GB pool allocation per call left the GPU idle for most of
     // a millisecond per work item of a library run; the budget is taken once.
-    void* f6_rec = nullptr; void* f6_sorted = nullptr; void* f6_femu = nullptr;
-    size_t f6_rec_bytes = 0, f6_sorted_bytes = 0, f6_femu_bytes = 0, f6_budget = 0;
+    void* f6_rec = nullptr; void* f6_sorted = nullptr; void* f6_femu = nullptr; void* f6_part = nullptr;
+    size_t f6_rec_bytes = 0, f6_sorted_bytes = 0, f6_femu_bytes = 0, f6_part_bytes = 0, f6_budget = 0;
 };
 
 struct HostTimer {   // adds the enclosing scope's host wall time to a stats field
@@ -576,12 +575,8 @@ template <int LT>
 int launch_file6_ws_t(Ctx* c, int blocks, const NucDev& nd, const double* d_Ein, const UbDev& ub, const F6WsArgs& a,
                       double* raw)
 {
-    if (c->f6_solo)
-        k_file6_cm_solo<LT><<<4 * c->sm_count, 128, 0, c->stream>>>(nd, d_Ein, ub, a.rec, a.sorted, a.femu, a.rmu, a.act,
-                                                                     a.a0, a.na, a.counter, raw);
-    else
-        k_file6_cm_ws<LT><<<blocks, F6_THREADS, 0, c->stream>>>(nd, d_Ein, ub, a.rec, a.sorted, a.femu, a.rmu, a.act,
-                                                                a.a0, a.na, a.counter, raw);
+    k_file6_cm_ws<LT><<<blocks, F6_THREADS, 0, c->stream>>>(nd, d_Ein, ub, a.rec, a.sorted, a.femu, a.rmu, a.act, a.a0,
+                                                            a.na, a.counter, raw);
     return 0;
 }
 
@@ -643,10 +638,14 @@ int file6_cm_ws(Ctx* c, Nuclide* n, Slot* s, const double* d_Ein, int NE, const 
     const size_t per_ein = (size_t)ub.maxU * M * sizeof(double);
     const size_t budget = std::max<size_t>(c->f6_budget, per_ein);
     const int nb = (int)std::min<size_t>({(size_t)n_act, std::max<size_t>(budget / per_ein, 1), (size_t)65535});
+    const int K = n->p.ne_per_grp;
+    const size_t part_bytes = (size_t)nb * G * K * L * sizeof(double);   // per-outgoing-energy integrals of a batch
     if (ctx_scratch(c, c->f6_rec, c->f6_rec_bytes, (size_t)nb * ub.maxU * sizeof(UbRec)) ||
         ctx_scratch(c, c->f6_sorted, c->f6_sorted_bytes, nb * sizeof(int)) ||
-        ctx_scratch(c, c->f6_femu, c->f6_femu_bytes, (size_t)nb * per_ein))
+        ctx_scratch(c, c->f6_femu, c->f6_femu_bytes, (size_t)nb * per_ein) ||
+        ctx_scratch(c, c->f6_part, c->f6_part_bytes, part_bytes))
         return 1;
+    double* const d_part = (double*)c->f6_part;
     UbRec* const d_rec = (UbRec*)c->f6_rec;
     int* const d_sorted = (int*)c->f6_sorted;
     double* const d_femu = (double*)c->f6_femu;
@@ -660,11 +659,15 @@ int file6_cm_ws(Ctx* c, Nuclide* n, Slot* s, const double* d_Ein, int NE, const 
         if (launch_check(c, "k_f6_femu")) return 1;
         F6WsArgs a{d_rec, d_sorted, d_femu, n->d_rmu.as<double>(), w.act.as<int>(),
                    a0, na, w.counter.as<unsigned long long>()};
-        const long long pairs = (long long)na * G;
+        const long long tasks = (long long)na * G * ((K + F6_CHUNK - 1) / F6_CHUNK);   // (E_in, group, chunk of outgoing energies)
         const int blocks = (int)std::min<long long>((long long)F6_BLOCKS_PER_SM * c->sm_count,
-                                                    (pairs + F6_CONS - 1) / F6_CONS);
-        if (launch_file6_ws(c, L, blocks, n->dev, d_Ein, ub, a, raw)) return 1;
+                                                    (tasks + F6_CONS - 1) / F6_CONS);
+        CK(c, cudaMemsetAsync(d_part, 0, (size_t)na * G * K * L * sizeof(double), c->stream));
+        if (launch_file6_ws(c, L, blocks, n->dev, d_Ein, ub, a, d_part)) return 1;
         if (launch_check(c, "k_file6_cm_ws")) return 1;
+        k_file6_reduce<<<blocks_for((long long)na * G * L, 256), 256, 0, c->stream>>>(n->dev, d_Ein, ub, w.act.as<int>(), a0,
+                                                                                     na, L, d_part, raw);
+        if (launch_check(c, "k_file6_reduce")) return 1;
     }
     return 0;
 }
@@ -991,8 +994,6 @@ int ndppgpu_init(int device, void** ctx)
         if (e && std::atoi(e) >= 1) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
         e = std::getenv("NDPPGPU_FG_QUEUE");
         if (e && std::atoll(e) >= 2) c->fg_queue_cap = std::atoll(e);
-        e = std::getenv("NDPPGPU_F6_SOLO");
-        c->f6_solo = e && e[0] == '1';
     }
     {
         cudaMemPool_t pool;
@@ -1012,7 +1013,7 @@ int ndppgpu_finalize(void* ctx)
     cudaStreamSynchronize(c->stream);
     for (auto& p : c->pending_all) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : c->pending_f6) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    for (void* p : {c->f6_rec, c->f6_sorted, c->f6_femu}) if (p) cudaFree(p);
+    for (void* p : {c->f6_rec, c->f6_sorted, c->f6_femu, c->f6_part}) if (p) cudaFree(p);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

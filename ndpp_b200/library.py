@@ -163,7 +163,7 @@ def run_c5(group, n_nuclides: int = 300, dist=None, policy: str = "lpt", tile_ro
                "measured_imbalance": k_max / (k_sum / world) if k_sum > 0 else None,
                "model_imbalance": {"lpt": imb if policy == "lpt" else plan(shapes, G, L, M, K, world, tile_rows)[1],
                                    "static": imb_static},
-               "root_process": {k: rep[k] for k in ("compute_s", "gather_s", "open_s_max", "integrate_s_max")},
+               "root_process": {k: rep[k] for k in ("compute_s", "gather_s", "open_s_max", "integrate_s_max", "alloc_s_max")},
                "gathered_bytes": group.gathered_bytes()}
         if keep is not None:    # e.g. the parity check of tests/util.py: the matrices are still on the root device
             keep(out, run, specs, parsed, e_bins, params)

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Builds named variants of libndppgpu.so for an A/B run on the GPU box.
 
-    python scripts/ab_build.py base= b4="-DF6_BLOCKS_PER_SM=4 -DF6_REG_PROD=40 -DF6_REG_CONS=88" plain="-DNDPP_FUSED_TABLELIN=0"
-    gpurun -- 'VARIANTS="base b4 plain base" CHECK=b4 bash scratch/ab_pf.sh'
+    python scripts/ab/ab_build.py base= b4="-DF6_BLOCKS_PER_SM=4 -DF6_REG_PROD=40 -DF6_REG_CONS=88" plain="-DNDPP_FUSED_TABLELIN=0"
+    gpurun -- 'VARIANTS="base b4 plain base" CHECK=b4 bash scripts/ab/ab_run.sh'
 
-Each NAME=FLAGS pair is compiled with the extra nvcc flags into scratch/libs/NAME.so (git-ignored, travels with gpurun);
-scratch/ab_pf.sh copies the variants over ndpp_b200/csrc/libndppgpu.so one after the other, runs bench.py on each and the
+Each NAME=FLAGS pair is compiled with the extra nvcc flags into scripts/ab/libs/NAME.so (git-ignored, travels with gpurun);
+scripts/ab/ab_run.sh copies the variants over ndpp_b200/csrc/libndppgpu.so one after the other, runs bench.py on each and the
 bit-identity / parity subset of the GPU tests on $CHECK.  The default library is rebuilt at the end.  Registers and spill
 of the dominant kernel are printed per variant (cuobjdump), so that a variant that cannot pay off is seen before any GPU
 time is spent."""
@@ -14,11 +14,11 @@ import shutil
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from ndpp_b200 import build as b  # noqa: E402
 
-LIBS = os.path.join(ROOT, "scratch", "libs")
+LIBS = os.path.join(ROOT, "scripts", "ab", "libs")
 
 
 def main(argv):

@@ -3,7 +3,8 @@
 // layer of include/ndpp_host.hpp exactly where preprocess_ndpp calls the Fortran routines
 // (src/ndpp.F90:607-609, 773-775) and writes the moment arrays to a result file.
 //
-//   ndpp_calc_scatt CASE RESULT [--device N]
+//   ndpp_calc_scatt CASE RESULT [--device N | --devices N]      --devices: N GPUs of this process (0 = all) work on the
+//                                                               nuclide together (ndppgpu_group_*, nuclide cases)
 //                   [--library FILE [--ascii] [--name ZAID] [--print-tol P] [--thin-tol T]]   nuclide cases only
 //                   [--library-only]
 //
@@ -97,7 +98,7 @@ void write_result(const char* path, double kind, int G, int L, const std::vector
 }
 
 struct Options {
-    int device = -1;
+    int device = -1, devices = -1;
     std::string library, name = "synthetic";
     bool ascii = false, library_only = false;
     double print_tol = 1.0e-8, thin_tol = 0.0;   // print_tol default of src/constants.F90; thin_tol as a fraction
@@ -122,7 +123,7 @@ void read_result(const char* path, int G, int L, std::vector<double>& el, std::v
     if (has_nu) take(ne_in * w, nu); else nu.clear();
 }
 
-void run_nuclide(const Context* ctx, Reader& r, const char* out, const Options& opt)
+void run_nuclide(const Context* ctx, const DeviceGroup* group, Reader& r, const char* out, const Options& opt)
 {
     Nuclide nuc;
     nuc.awr = r.num(); nuc.kT = r.num(); nuc.freegas_cutoff = r.num();
@@ -170,7 +171,9 @@ void run_nuclide(const Context* ctx, Reader& r, const char* out, const Options& 
     } else if (!opt.library.empty()) {
         // src/ndpp.F90:607-648 with the tolerance and the thinning on the device; tokeep = the group edges (:641-648)
         double compr = 0.0, err = 0.0;
-        ScattDataSet rxn_data(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
+        std::unique_ptr<ScattDataSet> set(group ? new ScattDataSet(*group, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st)
+                                                : new ScattDataSet(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st));
+        ScattDataSet& rxn_data = *set;
         rxn_data.calc_elastic_thinned(xe, opt.print_tol, opt.thin_tol, energy_bins, el_mat, compr, err);
         if (!xi.empty())
             rxn_data.calc_inelastic_thinned(xi, nuscatt, opt.print_tol, opt.thin_tol, energy_bins, inel_mat, nuinel_mat,
@@ -178,8 +181,12 @@ void run_nuclide(const Context* ctx, Reader& r, const char* out, const Options& 
         rxn_data.clear();
         write_result(out, KIND_NUCLIDE, G, L, el_mat, inel_mat, nuinel_mat);
     } else {
-        calc_scatt(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, Ein_el, Ein_inel, el_mat, inel_mat,
-                   nuinel_mat, st);
+        if (group)
+            calc_scatt(*group, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, Ein_el, Ein_inel, el_mat, inel_mat,
+                       nuinel_mat, st);
+        else
+            calc_scatt(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, Ein_el, Ein_inel, el_mat, inel_mat,
+                       nuinel_mat, st);
         write_result(out, KIND_NUCLIDE, G, L, el_mat, inel_mat, nuinel_mat);
     }
     if (!opt.library.empty()) {
@@ -220,7 +227,7 @@ void run_sab(const Context& ctx, Reader& r, const char* out)
 int main(int argc, char** argv)
 {
     try {
-        const char* usage = "usage: ndpp_calc_scatt CASE RESULT [--device N] [--library FILE [--ascii] [--name ZAID] "
+        const char* usage = "usage: ndpp_calc_scatt CASE RESULT [--device N | --devices N] [--library FILE [--ascii] [--name ZAID] "
                             "[--print-tol P] [--thin-tol T]] [--library-only]";
         if (argc < 3) fatal_error(usage);
         Options opt;
@@ -228,6 +235,7 @@ int main(int argc, char** argv)
             const std::string a = argv[i];
             auto value = [&]() -> const char* { if (i + 1 >= argc) fatal_error(usage); return argv[++i]; };
             if (a == "--device") opt.device = std::atoi(value());
+            else if (a == "--devices") opt.devices = std::atoi(value());
             else if (a == "--library") opt.library = value();
             else if (a == "--name") opt.name = value();
             else if (a == "--print-tol") opt.print_tol = std::atof(value());
@@ -241,12 +249,28 @@ int main(int argc, char** argv)
         const double kind = r.num();
         if (opt.library_only) {   // the writer alone: no device context
             if (kind != KIND_NUCLIDE) fatal_error("--library-only needs a nuclide case");
-            run_nuclide(nullptr, r, argv[2], opt);
+            run_nuclide(nullptr, nullptr, r, argv[2], opt);
             if (r.pos != r.a.size()) fatal_error("Case file has trailing data");
             return 0;
         }
+        if (opt.devices >= 0) {   // several GPUs of this process on the one nuclide
+            if (kind != KIND_NUCLIDE) fatal_error("--devices is implemented for nuclide cases");
+            DeviceGroup group(opt.devices);
+            run_nuclide(nullptr, &group, r, argv[2], opt);
+            if (r.pos != r.a.size()) fatal_error("Case file has trailing data");
+            long long evals = 0, launches = 0;
+            double ms = 0.0;
+            for (int d = 0; d < group.world(); ++d) {
+                const ndppgpu_stats_t s = group.stats(d);
+                evals += s.moment_evals; launches += s.launches; ms = s.kernel_ms > ms ? s.kernel_ms : ms;
+            }
+            std::printf(" %d devices: %lld moment evaluations, %lld kernel launches, %.3f ms on the busiest device, "
+                        "%lld bytes gathered over NCCL\n", group.world(), evals, launches, ms,
+                        ndppgpu_group_gathered_bytes(group.handle(), 0));
+            return 0;
+        }
         Context ctx(opt.device);
-        if (kind == KIND_NUCLIDE) run_nuclide(&ctx, r, argv[2], opt);
+        if (kind == KIND_NUCLIDE) run_nuclide(&ctx, nullptr, r, argv[2], opt);
         else if (kind == KIND_SAB) {
             if (!opt.library.empty()) fatal_error("--library is implemented for nuclide cases");
             run_sab(ctx, r, argv[2]);
