@@ -706,7 +706,8 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
         if (n_idx > 0) {
             const int rows = s->iso_rows ? 1 : 2;
             if (tmp_alloc(c, raw, (size_t)n_idx * rows * GL * 5 * sizeof(double))) return 1;
-            const long long tasks = (long long)n_idx * GL * 5;
+            const int LG = (n->L + FG_LW - 1) / FG_LW;   // groups of FG_LW Legendre orders walked together
+            const long long tasks = (long long)n_idx * n->G * LG * 5;
             if (tasks > 2000000000LL) return fail(c, "ndppgpu: too many free-gas cells in one call; split the E_in grid");
             // task list, heavy cells first
             TmpBuf d_tasks, d_heads, d_counter, d_frames, d_nvals, d_nchilds;
@@ -740,10 +741,10 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 const long long cap_tok = 4 * cap_items + 64;
                 const long long n_all = n_root + cap_items;
                 if (tmp_alloc(c, d_frames, warps * 2 * (capF / 2) * sizeof(FgPair) + sizeof(FgPair)) ||
-                    tmp_alloc(c, d_nvals, warps * capN * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
-                    tmp_alloc(c, d_items, (size_t)cap_items * sizeof(FgItem)) || tmp_alloc(c, d_ival, (size_t)n_all * sizeof(double)) ||
+                    tmp_alloc(c, d_nvals, warps * capN * FG_LW * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
+                    tmp_alloc(c, d_items, (size_t)cap_items * sizeof(FgItem)) || tmp_alloc(c, d_ival, (size_t)n_all * FG_LW * sizeof(double)) ||
                     tmp_alloc(c, d_roff, (size_t)n_all * sizeof(long long)) || tmp_alloc(c, d_rlen, (size_t)n_all * sizeof(int)) ||
-                    tmp_alloc(c, d_ops, (size_t)cap_tok) || tmp_alloc(c, d_pay, (size_t)cap_tok * sizeof(double)))
+                    tmp_alloc(c, d_ops, (size_t)cap_tok) || tmp_alloc(c, d_pay, (size_t)cap_tok * FG_LW * sizeof(double)))
                     return 1;
                 CK(c, cudaMemsetAsync(d_ovf.p, 0, sizeof(int), c->stream));
                 CK(c, cudaMemsetAsync(d_tails.p, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -759,7 +760,8 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                     const long long lo = bounds[bounds.size() - 2], hi = bounds.back();
                     const int blocks = (int)std::min<long long>(max_blocks, (hi - lo + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
                     CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
-                    k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, 0, c->stream>>>(
+                    CK(c, cudaFuncSetAttribute(k_freegas_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgShared)));
+                    k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
                         n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q, lo, hi,
                         d_counter.as<unsigned long long>(), d_frames.as<FgPair>(), d_nvals.as<double>(), d_nchilds.as<int>(),
                         (int)capF, (int)capN, d_ovf.as<int>());
@@ -787,10 +789,10 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 // items that referred to later generations: evaluate their programs, last generation first
                 for (int g = (int)bounds.size() - 3; g >= 0; --g) {
                     const long long lo = bounds[g], hi = bounds[g + 1];
-                    k_fg_combine<<<blocks_for(hi - lo, 256), 256, 0, c->stream>>>(q, lo, hi);
+                    k_fg_combine<<<blocks_for((hi - lo) * FG_LW, 256), 256, 0, c->stream>>>(q, lo, hi);
                     if (launch_check(c, "k_fg_combine")) return 1;
                 }
-                k_fg_store<<<blocks_for(n_root, 256), 256, 0, c->stream>>>(q, rows, n->G, n->L, raw.as<double>());
+                k_fg_store<<<blocks_for(n_root * FG_LW, 256), 256, 0, c->stream>>>(q, rows, n->G, n->L, raw.as<double>());
                 if (launch_check(c, "k_fg_store")) return 1;
                 c->stats.freegas_items += bounds.back();
                 break;
@@ -798,7 +800,7 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             k_freegas_finish<<<blocks_for((long long)n_idx * 32, 128), 128, 0, c->stream>>>(
                 n->dev, s->dev, d_Ein, idx.as<int>(), n_idx, rows, raw.as<double>(), d_out);
             if (launch_check(c, "k_freegas_finish")) return 1;
-            c->stats.freegas_tasks += tasks;
+            c->stats.freegas_tasks += (long long)n_idx * GL * 5;   // adaptive (E_in, g, l, sub) integrations, as the reference counts them
         }
     }
     k_copy_top<<<1, 256, 0, c->stream>>>(d_Ein, NE, n->e_bins.back(), GL, d_out, nullptr);

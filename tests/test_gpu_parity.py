@@ -189,12 +189,13 @@ def test_c3_freegas(scatt, oracle, kT):
     sub = Ein[[0, 333, 700, 940, 999]]  # the last point equals the cutoff: target-at-rest branch
     got, ref = dn.elastic(sub), rn.elastic(sub)
     assert np.allclose(ref[:, :, 0].sum(axis=1), 1.0, atol=1e-12)
-    # the adaptive integrator takes accept/split decisions on exp(); libdevice and glibc may differ
-    # in the last bit, so allow a handful of cells at the integrator's own tolerance
+    # the adaptive integrator takes its accept / split decisions on exp(): the device evaluates it with the host libm's
+    # bits (csrc/libm_exact.cuh), walks every order's own tree and keeps its association, so not a cell may leave the
+    # tolerance (measured: max |d| 8e-17 with libdevice's exp, before the exact one)
     err = np.abs(got - ref)
     ok = (err <= 1e-9 * np.abs(ref)) | (err <= 1e-12)
-    assert np.count_nonzero(~ok) <= 0.002 * ok.size, f"{np.count_nonzero(~ok)} cells outside tolerance"
-    assert err.max() < 1e-6
+    assert np.count_nonzero(~ok) == 0, f"{np.count_nonzero(~ok)} cells outside tolerance"
+    assert err.max() < 1e-13
 
 
 def test_freegas_heavy_target_two_rows(scatt, oracle):
@@ -210,8 +211,8 @@ def test_freegas_heavy_target_two_rows(scatt, oracle):
     got, ref = dn.elastic(sub), rn.elastic(sub)
     err = np.abs(got - ref)
     ok = (err <= 1e-9 * np.abs(ref)) | (err <= 1e-12)
-    assert np.count_nonzero(~ok) <= 0.002 * ok.size
-    assert err.max() < 1e-6
+    assert np.count_nonzero(~ok) == 0
+    assert err.max() < 1e-13
 
 
 @pytest.mark.parametrize("mode,elastic", [("skewed", None), ("equal", "coherent"), ("cont", "incoherent")])
@@ -440,7 +441,7 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=1000)
     Ein = Ein[[0, 450, 900]]
     outs, items = [], []
-    for split, queue in (("4", None), ("3", None), ("2", None), ("1", None), ("2", "512")):
+    for split, queue in (("3", None), ("2", None), ("1", None), ("2", "512")):
         monkeypatch.setenv("NDPPGPU_FG_SPLIT", split)
         if queue is None:
             monkeypatch.delenv("NDPPGPU_FG_QUEUE", raising=False)
@@ -454,7 +455,7 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     assert np.any(outs[0] != 0)
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
-    assert items[0] < items[1] < items[2] < items[3] and items[4] == items[2]
+    assert items[0] < items[1] < items[2] and items[3] == items[1]
 
 
 def test_unitbase_and_file6_cm_leg_heavy_target_limit(scatt, oracle):
@@ -487,7 +488,7 @@ def test_freegas_p0_matches_the_analytic_kernel_for_A1(scatt):
 def test_cuda_against_the_committed_walk_vectors(scatt):
     """The CUDA path against tests/golden/walk_vectors.npz: moments computed by literal walks of the Fortran text
     (scripts/make_walk_golden.py) with neither the oracle's integrators nor CUDA -- free gas at the reference's default
-    adaptive tolerances (same allowance as test_c3_freegas for accept / split decisions taken on exp()), and the Law-44
+    adaptive tolerances, and the Law-44
     continuum through unit-base interpolation + integrate_file6_cm_leg (device-converted tables)."""
     import importlib.util
     import os
@@ -501,7 +502,7 @@ def test_cuda_against_the_committed_walk_vectors(scatt):
     ref = v["freegas_moments"]
     err = np.abs(got - ref)
     ok = (err <= 1e-9 * np.abs(ref)) | (err <= 1e-12)
-    assert np.count_nonzero(~ok) <= 2 and err.max() < 1e-6
+    assert np.count_nonzero(~ok) == 0 and err.max() < 1e-13
     nuc, e_bins, params = mk.file6_case()
     dn = scatt.DeviceNuclide(nuc, e_bins, params)
     for E, ref in zip(v["file6_Ein"], v["file6_moments"]):
