@@ -1,34 +1,42 @@
 #!/usr/bin/env python
-"""One small invocation of a single path, for ncu captures (kept short: ncu replays every kernel)."""
+"""One pass of one BASELINE configuration through the C-ABI, for profiling under ncu (never for timing):
+    python scripts/profile_case.py --case c1|c2|c3|c4d|c4c [--n N]
+c2: U-238 shape (--n = grid points, default 20000); c3: H-1 free gas (--n = E_in points, default 1000);
+c4d / c4c: S(a,b) discrete / continuous; c1: the tests/test_scatt fixture."""
 import argparse
 import os
 import sys
 
-import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ndpp_b200 import ace, egrid, scatt, synth  # noqa: E402
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--case", default="c3")
-ap.add_argument("--n", type=int, default=40)
-a = ap.parse_args()
-if a.case == "c3":
-    nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=a.n)
-    dn = scatt.DeviceNuclide(nuc, e_bins, params)
-    out = dn.elastic(Ein)
-    print("c3", out.shape, float(out[:, :, 0].sum()))
-elif a.case == "c4":
-    sab = synth.c4_sab("skewed")
-    e_bins = synth.group_structure(70)
-    out = scatt.DeviceSab(sab).calc(e_bins, 0, 5, egrid.sab_egrid(sab, e_bins))
-    print("c4", out.shape)
-elif a.case == "c2levels":
-    nuc = synth.heavy_nuclide(n_grid=a.n * 50, with_continuum=False)
-    e_bins = synth.group_structure(70)
-    dn = scatt.DeviceNuclide(nuc, e_bins, ace.Params(order=7))
-    thr = min(nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT != 2)
-    out, _ = dn.inelastic(nuc.energy[nuc.energy >= thr])
-    el = dn.elastic(nuc.energy)
-    print("c2levels", out.shape, el.shape)
-print(scatt.default_context().stats())
+def main():
+    from ndpp_b200 import ace, egrid, scatt, synth
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", required=True)
+    ap.add_argument("--n", type=int, default=0)
+    a = ap.parse_args()
+    if a.case == "c1":
+        nuc, e_bins, params = synth.c1_fixture()
+        Ein = synth.c1_ein_grid(997)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params)
+        dn.elastic(Ein), dn.inelastic(Ein)
+    elif a.case == "c2":
+        nuc, e_bins, params, Eel, Einel = synth.c2_u238(n_grid=a.n or 20000)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params)
+        dn.elastic(Eel), dn.inelastic(Einel)
+    elif a.case == "c3":
+        nuc, e_bins, params, Ein = synth.c3_h1_freegas()
+        dn = scatt.DeviceNuclide(nuc, e_bins, params)
+        dn.elastic(Ein[:: max(1, len(Ein) // (a.n or len(Ein)))])
+    elif a.case in ("c4d", "c4c"):
+        sab = synth.c4_sab("skewed") if a.case == "c4d" else synth.c4_sab("cont", n_eout=400)
+        e_bins = synth.group_structure(70)
+        scatt.calc_scattsab(sab, e_bins, ace.SCATT_TYPE_LEGENDRE, 5, 2001, egrid.sab_egrid(sab, e_bins))
+    else:
+        raise SystemExit("unknown case")
+
+
+if __name__ == "__main__":
+    main()

@@ -182,7 +182,7 @@ def test_law9_and_law4_lab(scatt, oracle):
     assert_parity(gn, rnu, what="law 9 + law 4 lab (nu)")
 
 
-@pytest.mark.parametrize("kT", [synth.KT_293K, synth.KT_1200K])
+@pytest.mark.parametrize("kT", [synth.KT_293K, synth.KT_600K, synth.KT_1200K])
 def test_c3_freegas(scatt, oracle, kT):
     nuc, e_bins, params, Ein = synth.c3_h1_freegas(kT=kT, n_ein=1000)
     dn, rn = _pair(scatt, oracle, nuc, e_bins, params)
@@ -511,3 +511,69 @@ def test_cuda_against_the_committed_walk_vectors(scatt):
         # the walk integrates the mu segments by Gauss-Legendre quadrature instead of the closed forms, whose
         # round-off (up to ~3e-9 of the segment's P0 at this mu spacing) is the reference's own: 1e-8 of P0 = 1
         assert np.all(np.abs(m - ref) <= 1e-9 * np.abs(ref) + 1e-8), float(E)
+
+
+def test_cuda_against_the_committed_vectors_of_the_other_unpinned_routines(scatt):
+    """The CUDA path against tests/golden/walk_vectors_rest.npz: independent numpy evaluations (tests/walks.py) of the
+    routines for which the reference holds no test -- S(a,b) elastic / discrete / continuous + combine_sab_grid, law 9,
+    integrate_file6_lab_leg, thin_grid, apply_tol_scatt -- so that their GPU evidence does not pass through the C
+    restatement."""
+    from tests.util import check_against_rest_vectors
+
+    def sab_calc(sab, e_bins, order, E, parts):
+        ds = scatt.DeviceSab(sab)
+        out = ds.calc(e_bins, ace.SCATT_TYPE_LEGENDRE, order, E, parts=parts)
+        ds.clear()
+        return out
+
+    def inelastic_of(nuc, e_bins, params, E):
+        dn = scatt.DeviceNuclide(nuc, e_bins, params)
+        out = dn.inelastic(np.asarray(E, dtype=float))[0]
+        dn.clear()
+        return out
+
+    def thin(x, y, tokeep, tol):
+        xk = scatt.thin_grid(x, y, tokeep, tol)[0]
+        return np.searchsorted(x, xk)
+    check_against_rest_vectors(sab_calc, inelastic_of, thin, lambda d, tol: scatt.apply_tol_scatt(d.copy(), tol))
+
+
+@pytest.mark.parametrize("index", [0, 1, 2, 7, 11])
+def test_c5_sampled_nuclides_of_every_shape(scatt, oracle, index):
+    """BASELINE configs[4]: nuclides of the synthetic 300-nuclide library, one or two of each shape (light: elastic only;
+    medium: 10 levels + Law-44 continuum; heavy: C2 shape; awr from 1.3 to 236), P5, 70 groups, on sampled E_in of their
+    own grids against the oracle -- device-converted tables, strict tolerance."""
+    spec = synth.c5_library(300)[index]
+    nuc, Eel, Einel = synth.c5_nuclide(spec)
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=5, mu_bins=2001)
+    dn, rn = _pair(scatt, oracle, nuc, e_bins, params)
+    rng = np.random.default_rng(500 + index)
+    ke = np.sort(rng.choice(len(Eel), 24, replace=False))
+    assert_parity(dn.elastic(Eel[ke]), rn.elastic(Eel[ke]), what=f"C5 nuclide {index} ({spec[1]}) elastic")
+    if Einel is not None:
+        ki = np.sort(rng.choice(len(Einel), 16, replace=False))
+        ri = rn.inelastic(Einel[ki])[0]
+        assert np.any(ri != 0)
+        assert_parity(dn.inelastic(Einel[ki])[0], ri, what=f"C5 nuclide {index} ({spec[1]}) inelastic")
+
+
+def test_shapes_of_the_sampled_c5_nuclides():
+    assert {synth.c5_library(300)[i][1] for i in (0, 1, 2, 7, 11)} == {"light", "medium", "heavy"}
+
+
+def test_freegas_column_with_non_positive_elastic_xs_is_zero(scatt, oracle):
+    """Below the free-gas cutoff k_elastic leaves the column to the free-gas kernels, which only write columns whose
+    interpolated elastic cross section is positive (scatt_interp_distro returns distro = ZERO otherwise,
+    src/scattdata_header.F90:414-419): such a column must come back as zeros, not as whatever the buffer held."""
+    nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=40)
+    nuc.elastic = nuc.elastic.copy()
+    nuc.elastic[:30] = 0.0                       # sigma_s = 0 over the low end of the grid
+    dn, rn = _pair(scatt, oracle, nuc, e_bins, params)
+    E = np.array([nuc.energy[3] * 1.3, nuc.energy[12], Ein[25], Ein[30]])
+    for _ in range(2):                           # the second call re-uses the pool's (now dirty) memory
+        got = dn.elastic(E)
+    ref = rn.elastic(E)
+    assert np.all(ref[:2] == 0.0) and np.any(ref[2:] != 0.0)
+    assert np.array_equal(got[:2], ref[:2])
+    assert_parity(got, ref, what="free gas with a vanishing elastic xs")

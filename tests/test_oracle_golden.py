@@ -399,179 +399,68 @@ def test_freegas_p0_matches_the_analytic_kernel_for_A1(oracle, x):
 @pytest.mark.parametrize("Ein", [1.2, 3.3, 9.0, 20.0])
 def test_law9_matches_numerical_integration_of_the_evaporation_spectrum(oracle, Ein):
     """law9_scatter_lab_leg (src/scattdata_header.F90:1274-1326) has no reference test (parity unpinned): its group
-    probabilities are the integrals of E' exp(-E'/T) up to E - U, checked here by numerical quadrature, and its
-    angular moments those of the laboratory angular table (linear: P1/P0 = b/3, higher moments 0)."""
-    from scipy import integrate
-    b = 0.45
-    energy = np.geomspace(1e-11, 20.0, 80)
-    thr = int(np.searchsorted(energy, 1.0)) + 1
-    e0 = energy[thr - 1]
-    e9, T9, U = np.array([e0, 5.0, 20.0]), np.array([0.3, 0.6, 1.1]), 0.4
-    d9 = np.concatenate([[0.0, 3.0], e9, T9, [U]])
-    blk = np.array([2.0, 2.0, -1.0, 1.0, 0.5 * (1 - b), 0.5 * (1 + b), 0.0, 1.0])      # lin-lin, 2 points
-    # the angular table is read on the energy grid of the law-9 block (scattdata_header.F90:342-368), so it has its rows
-    ad = ace.DistAngle(energy=e9.copy(), type=np.array([ace.ANGLE_TABULAR] * 3, np.int32),
-                       location=np.array([1, 9, 17], np.int32), data=np.concatenate([[0.0], blk, blk, blk]))
-    pv = ace.Tab1(x=np.array([e0, 20.0]), y=np.array([1.0, 1.0]))
-    r9 = ace.Reaction(MT=16, Q_value=-0.9, threshold=thr, scatter_in_cm=False, multiplicity=1,
-                      sigma=np.ones(len(energy) - thr + 1), adist=ad, edist=ace.DistEnergy(law=9, data=d9, p_valid=pv))
-    nuc = ace.Nuclide(awr=26.7, kT=0.0, energy=energy, elastic=np.full(len(energy), 2.0),
-                      reactions=[ace.Reaction(MT=2, threshold=1), r9])
-    e_bins = synth.group_structure(20, 1e-4, 20.0)
-    rn = oracle.RefNuclide(nuc, e_bins, ace.Params(order=4, mu_bins=401))
+    probabilities are the integrals of E' exp(-E'/T) up to E - U, checked here by numerical quadrature (tests/walks.py),
+    and its angular moments those of the laboratory angular table (linear: P1/P0 = b/3, higher moments 0)."""
+    from tests import walks
+    nuc, e_bins, params, spec, _ = walks.law9_case()
+    rn = oracle.RefNuclide(nuc, e_bins, params)
     rn.convert_distro()
     m = rn.inelastic(np.array([Ein]))[0][0]
-    T = float(np.interp(Ein, e9, T9))
-    top = Ein - U
-    norm = integrate.quad(lambda e: e * np.exp(-e / T), 0.0, top, epsabs=0, epsrel=1e-13)[0]
-    p = np.array([integrate.quad(lambda e: e * np.exp(-e / T), min(lo, top), min(hi, top), epsabs=0, epsrel=1e-13)[0]
-                  for lo, hi in zip(e_bins[:-1], e_bins[1:])]) / norm
+    p = walks.walk_law9(e_bins, spec, Ein)
     assert np.allclose(m[:, 0], p, rtol=1e-9, atol=1e-13)
     nz = p > 1e-12
-    assert np.allclose(m[nz, 1] / m[nz, 0], b / 3.0, rtol=1e-8)
+    assert np.allclose(m[nz, 1] / m[nz, 0], walks.LAW9_B / 3.0, rtol=1e-8)
     assert np.all(np.abs(m[nz, 2:] / m[nz, :1]) < 1e-8)
 
 
 def test_file6_lab_leg_bin_counting_follows_the_reference_text(oracle):
-    """integrate_file6_lab_leg (src/scattdata_header.F90:1334-1450) is parity unpinned beyond its single-E_out branch.
-    Hand evaluation of the Fortran text on a uniform pdf (41 E_out points on [0, 2], every pdf(i)*dE(i) = 0.025) and the
-    group edges (0, 0.2, 0.5, 0.9, 1.4, 5):  a lower edge adds f_lo * bin (the part *below* the edge, :1385-1391) and then
-    starts at the next bin, an upper edge adds f_hi * bin; edges that coincide with an E_out point have f = 0, and
-    linspace puts E_out(29) just above 1.4 (f = 1 on bin 28 for both neighbours).  Bins counted per group: 3, 5, 7, 9, 13;
-    the final normalisation (:1447-1448) divides by their sum, 37.  The angular part is the table's: P1/P0 = b/3."""
-    from tests.util import heavy_limit_law61
-    nuc, e_bins, params, _ = heavy_limit_law61(awr=55.0, uniform=True)
-    nuc.reactions[1].scatter_in_cm = False
+    """integrate_file6_lab_leg (src/scattdata_header.F90:1334-1450) is parity unpinned beyond its single-E_out branch:
+    hand evaluation of the Fortran text on a uniform pdf (tests/walks.py: walk_file6_lab)."""
+    from tests import walks
+    nuc, e_bins, params, Ein = walks.file6_lab_case()
     rn = oracle.RefNuclide(nuc, e_bins, params)
     rn.convert_distro()
-    m = rn.inelastic(np.array([3.0]))[0][0]
-    assert np.linspace(0.0, 2.0, 41)[28] > 1.4
-    assert np.allclose(m[:, 0], np.array([3.0, 5.0, 7.0, 9.0, 13.0]) / 37.0, rtol=0, atol=1e-12)
-    assert np.allclose(m[:, 1] / m[:, 0], 0.2, rtol=1e-9) and np.all(np.abs(m[:, 2:]) < 1e-9)
+    m = rn.inelastic(Ein)[0][0]
+    p0, ratio = walks.walk_file6_lab()
+    assert np.allclose(m[:, 0], p0, rtol=0, atol=1e-12)
+    assert np.allclose(m[:, 1] / m[:, 0], ratio, rtol=1e-9) and np.all(np.abs(m[:, 2:]) < 1e-9)
 
 
 @pytest.mark.parametrize("mode", ["equal", "skewed"])
 def test_sab_discrete_inelastic_against_a_numpy_evaluation(oracle, mode):
     """integrate_sab_inel_disc + combine_sab_grid (src/sab.F90:142-245, 415-454) have no reference test (parity
-    unpinned).  Without an elastic part the combined matrix is sum_{E_out in g} w_j sum_k P_l(mu_jk) over the
-    interpolated table row, divided by its P0 total; evaluated here with numpy's Legendre polynomials, not the
-    reference's explicit ones."""
-    from numpy.polynomial import legendre as npleg
-    sab = synth.c4_sab(mode=mode, elastic=None, n_ein=20, n_eout=16, n_mu=8)
-    e_bins = synth.group_structure(30, 1e-10, 1e-5)
-    rng = np.random.default_rng(8)
-    ein = np.asarray(sab.inelastic_e_in)
-    E = np.sort(np.concatenate([ein[[3, 11]], np.exp(rng.uniform(np.log(ein[0]), np.log(ein[-1]), 12))]))
+    unpinned): evaluated with numpy's Legendre polynomials, not the reference's explicit ones (tests/walks.py)."""
+    from tests import walks
+    sab, e_bins, E = walks.sab_discrete_case(mode)
     got = oracle.sab_calc(sab, e_bins, 5, E)
-    eo, mu = np.asarray(sab.inelastic_e_out), np.asarray(sab.inelastic_mu)    # [iEin][iEout], [iEin][iEout][imu]
-    n_out, n_mu = eo.shape[1], mu.shape[2]
-    w = np.ones(n_out)
-    if mode == "skewed":
-        w[[0, -1]], w[[1, -2]] = 0.1, 0.4
-    w = w / (w.sum() * n_mu)
+    ref = walks.walk_sab_discrete(sab, e_bins, E, mode)
     assert np.array_equal(got[-1], got[-2])          # the last column copies its predecessor (src/sab.F90:452)
-    for i, e in enumerate(E[:-1]):
-        k = min(int(np.searchsorted(ein, e, side="right")) - 1, len(ein) - 2)
-        f = (e - ein[k]) / (ein[k + 1] - ein[k])
-        eo_i = (1 - f) * eo[k] + f * eo[k + 1]
-        mu_i = (1 - f) * mu[k] + f * mu[k + 1]
-        ref = np.zeros((len(e_bins) - 1, 6))
-        for j in range(n_out):
-            if e_bins[0] <= eo_i[j] < e_bins[-1]:
-                g = int(np.searchsorted(e_bins, eo_i[j], side="right")) - 1
-                for l in range(6):
-                    ref[g, l] += w[j] * npleg.legval(mu_i[j], [0] * l + [1]).sum()
-        ref /= ref[:, 0].sum()
-        assert np.allclose(got[i], ref, rtol=1e-11, atol=1e-13), (mode, i)
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-13), mode
 
 
 @pytest.mark.parametrize("elastic", ["coherent", "incoherent"])
 def test_sab_elastic_and_combination_against_a_numpy_evaluation(oracle, elastic):
-    """integrate_sab_el (src/sab.F90:21-109: coherent = one cosine 1 - E_bragg/E weighted P/E, incoherent = equally
-    likely interpolated cosines weighted by the interpolated P) and combine_sab_grid ((el + inel) / sum_g P0, :415-454),
-    evaluated independently with numpy."""
-    from numpy.polynomial import legendre as npleg
-    sab = synth.c4_sab(mode="equal", elastic=elastic, n_ein=20, n_eout=16, n_mu=8)
-    e_bins = synth.group_structure(30, 1e-10, 1e-5)
-    rng = np.random.default_rng(9)
-    ee, P = np.asarray(sab.elastic_e_in), np.asarray(sab.elastic_P)
-    E = np.sort(np.exp(rng.uniform(np.log(ee[0] * 1.01), np.log(ee[-1] * 0.99), 15)))
+    """integrate_sab_el (src/sab.F90:21-109) and combine_sab_grid ((el + inel) / sum_g P0, :415-454), evaluated
+    independently with numpy (tests/walks.py)."""
+    from tests import walks
+    sab, e_bins, E = walks.sab_elastic_case(elastic)
     out, el, inel = oracle.sab_calc(sab, e_bins, 5, E, parts=True)
-    for i, e in enumerate(E[:-1]):
-        k = int(np.searchsorted(ee, e, side="right")) - 1
-        f = (e - ee[k]) / (ee[k + 1] - ee[k])
-        g = int(np.searchsorted(e_bins, e, side="right")) - 1
-        ref = np.zeros((len(e_bins) - 1, 6))
-        if elastic == "coherent":
-            mu = np.array([1.0 - ee[k] / e])
-            sig, w = P[k] / e, 1.0
-        else:
-            em = np.asarray(sab.elastic_mu)
-            mu = (1 - f) * em[k] + f * em[k + 1]
-            sig, w = (1 - f) * P[k] + f * P[k + 1], 1.0 / em.shape[1]
-        for l in range(6):
-            ref[g, l] = sig * w * npleg.legval(mu, [0] * l + [1]).sum()
-        assert np.allclose(el[i], ref, rtol=1e-11, atol=1e-13 * sig), (elastic, i)
+    ref, sig = walks.walk_sab_elastic(sab, e_bins, E, elastic)
+    for i in range(len(E) - 1):
+        assert np.allclose(el[i], ref[i], rtol=1e-11, atol=1e-13 * sig[i]), (elastic, i)
         tot = el[i] + inel[i]
         assert np.allclose(out[i], tot / tot[:, 0].sum(), rtol=1e-12, atol=1e-15)
 
 
 def test_sab_continuous_inelastic_against_a_numpy_evaluation(oracle):
-    """integrate_sab_inel_cont (src/sab.F90:253-408, parity unpinned): stage 1 integrates every table row over the
-    groups with the weights pdf(i) * dE(i) and the edge rule of the text (f * bin at both edges, cosines interpolated to
-    the edge), stage 2 interpolates linearly to E_in and scales with the interpolated sigma.  Evaluated with numpy."""
-    from numpy.polynomial import legendre as npleg
-    sab = synth.c4_sab(mode="cont", elastic=None, n_ein=10, n_eout=70, n_mu=6)
-    e_bins = synth.group_structure(24, 1e-10, 1e-5)
-    G, L = len(e_bins) - 1, 6
-    ein, sg = np.asarray(sab.inelastic_e_in), np.asarray(sab.inelastic_sigma)
-
-    def pl(mu):                      # sum over the cosines of P_0..P_5
-        return np.array([npleg.legval(mu, [0] * l + [1]).sum() for l in range(L)])
-
-    def bsearch(a, v):               # 0-based lower index, v == last -> n-2 (src/search.F90)
-        return min(int(np.searchsorted(a, v, side="right")) - 1, len(a) - 2)
-
-    rows = []
-    for d in sab.inelastic_data:
-        Eo, mu = np.asarray(d.e_out), np.asarray(d.mu)        # mu[iEout][imu]
-        w = np.append(np.asarray(d.e_out_pdf)[:-1] * np.diff(Eo), 0.0)
-        dist = np.zeros((G, L))
-        for g in range(G):
-            lo_e, hi_e = e_bins[g], e_bins[g + 1]
-            acc = np.zeros(L)
-            if lo_e < Eo[0]:
-                i_lo = 0
-            elif lo_e >= Eo[-1]:
-                continue
-            else:
-                i = bsearch(Eo, lo_e)
-                f = (lo_e - Eo[i]) / (Eo[i + 1] - Eo[i])
-                acc += f * w[i] * pl((1 - f) * mu[i] + f * mu[i + 1])
-                i_lo = i + 1
-            if hi_e < Eo[0]:
-                continue
-            elif hi_e >= Eo[-1]:
-                i_hi = len(Eo) - 2
-            else:
-                i = bsearch(Eo, hi_e)
-                f = (hi_e - Eo[i]) / (Eo[i + 1] - Eo[i])
-                acc += f * w[i] * pl((1 - f) * mu[i] + f * mu[i + 1])
-                i_hi = i - 1
-            for i in range(i_lo, i_hi + 1):
-                acc += w[i] * pl(mu[i])
-            dist[g] = acc / mu.shape[1]
-        rows.append(dist)
-    rows = np.array(rows)
-    rng = np.random.default_rng(10)
-    E = np.sort(np.concatenate([ein[[2]], np.exp(rng.uniform(np.log(ein[0]), np.log(ein[-1] * 0.999), 10))]))
+    """integrate_sab_inel_cont (src/sab.F90:253-408, parity unpinned), evaluated with numpy (tests/walks.py)."""
+    from tests import walks
+    sab, e_bins, E = walks.sab_continuous_case()
+    sg = np.asarray(sab.inelastic_sigma)
     out, el, inel = oracle.sab_calc(sab, e_bins, 5, E, parts=True)
-    for i, e in enumerate(E[:-1]):
-        k = bsearch(ein, e)
-        f = (e - ein[k]) / (ein[k + 1] - ein[k])
-        ref = ((1 - f) * rows[k] + f * rows[k + 1]) * ((1 - f) * sg[k] + f * sg[k + 1])
-        assert np.allclose(inel[i], ref, rtol=1e-10, atol=1e-12 * sg[k]), i
-        assert np.allclose(out[i], ref / ref[:, 0].sum(), rtol=1e-10, atol=1e-13)
+    r_inel, r_out = walks.walk_sab_continuous(sab, e_bins, E)
+    assert np.allclose(inel[:-1], r_inel[:-1], rtol=1e-10, atol=1e-12 * sg.max())
+    assert np.allclose(out, r_out, rtol=1e-10, atol=1e-13)
 
 
 @pytest.mark.parametrize("A", [3.5, 15.858])
@@ -633,55 +522,22 @@ def test_freegas_angular_moments_match_a_double_integral_of_the_kernel(oracle, A
 
 
 def test_thin_grid_kept_points_equal_a_numpy_walk_of_the_text(oracle):
-    """thin_grid_one (src/thin.F90:51-169, no reference test) walked literally in numpy: point k is tested against
-    (last kept, k + 1) with log-x interpolation, the error is divided by y *with its sign* (:125-127: a negative y makes
-    any error acceptable), points in `tokeep` stay.  The kept set and the compression must be identical."""
-    rng = np.random.default_rng(21)
-    x = np.geomspace(1e-6, 20.0, 400)
-    y = (np.sin(2.0 * np.log(x))[:, None] + 0.3) * np.linspace(1.0, 2.0, 10)[None, :]      # changes sign
-    y += 1e-4 * rng.normal(size=y.shape)
-    y[50:60] = 0.0                                                                         # y == 0: absolute error
-    tokeep = np.array([x[123], 7.0])
-    tol = 5e-3
+    """thin_grid_one (src/thin.F90:51-169, no reference test) walked literally in numpy (tests/walks.py).  The kept set
+    and the compression must be identical."""
+    from tests import walks
+    x, y, tokeep, tol = walks.thin_case()
     keep, comp, _, _ = oracle.thin_grid(x, y, tokeep, tol)
-    ref = [0]
-    klo, k = 0, 1
-    while k + 1 < len(x):
-        frac = 1.0 / np.log(x[k + 1] / x[klo]) * np.log(x[k] / x[klo])
-        removable = not np.any(tokeep == x[k])
-        if removable:
-            t = y[klo] + (y[k + 1] - y[klo]) * frac
-            err = np.abs(t - y[k])
-            nz = y[k] != 0.0
-            err[nz] = err[nz] / y[k][nz]
-            removable = bool(np.all(err <= tol))
-        if not removable:
-            ref.append(k)
-            klo = k
-        k += 1
-    ref.append(len(x) - 1)
+    ref = walks.walk_thin_grid(x, y, tokeep, tol)
     assert np.array_equal(keep, ref)
     assert comp == (len(x) - len(ref)) / len(x) and 0.2 < comp < 1.0
 
 
 def test_apply_tol_scatt_equals_a_numpy_evaluation_of_the_text(oracle):
-    """apply_tol_scatt (src/scatt.F90:786-818) evaluated in numpy: groups with 0 < P0 < tol are zeroed for every order,
-    then the column is scaled by orig_total / new_total (0 when orig_total <= 0)."""
-    rng = np.random.default_rng(22)
-    d = rng.normal(size=(60, 11, 5)) * 0.2
-    d[:, :, 0] = np.abs(d[:, :, 0]) * (rng.uniform(size=(60, 11)) > 0.2)
-    d[::4, 3, 0] = 4e-9
-    d[7] = 0.0
-    d[9, :, 0] = 0.0                      # orig_total = 0 with non-zero higher moments: norm = 0 wipes the column
-    tol = 1e-8
-    ref = d.copy()
-    for i in range(len(ref)):
-        orig = ref[i, :, 0].sum()
-        small = (ref[i, :, 0] > 0.0) & (ref[i, :, 0] < tol)
-        ref[i, small, :] = 0.0
-        ref[i] *= (orig / ref[i, :, 0].sum()) if orig > 0.0 else 0.0
+    """apply_tol_scatt (src/scatt.F90:786-818) evaluated in numpy (tests/walks.py)."""
+    from tests import walks
+    d, tol = walks.tol_case()
     got = oracle.apply_tol_scatt(d, tol)
-    assert np.allclose(got, ref, rtol=1e-15, atol=0.0) and np.all(got[9] == 0.0)
+    assert np.allclose(got, walks.walk_apply_tol(d, tol), rtol=1e-15, atol=0.0) and np.all(got[9] == 0.0)
 
 
 def _walk_file4_cm_leg(fw, Ein, awr, Q, E_bins, w, L):
@@ -1031,3 +887,32 @@ def test_oracle_reproduces_the_committed_walk_vectors(oracle):
         got = rn.interp_distro(int(v["file6_slot"]), float(E))
         got = got / got[:, 0].sum()
         assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref) + 1e-9)
+
+
+def test_oracle_reproduces_the_committed_vectors_of_the_other_unpinned_routines(oracle):
+    """tests/golden/walk_vectors_rest.npz (scripts/make_walk_golden_rest.py): S(a,b) elastic / discrete / continuous and
+    their combination, law 9, integrate_file6_lab_leg, thin_grid, apply_tol_scatt -- independent numpy evaluations,
+    committed; the CUDA path is compared with the same file in tests/test_gpu_parity.py."""
+    from tests.util import check_against_rest_vectors
+
+    def inelastic_of(nuc, e_bins, params, E):
+        rn = oracle.RefNuclide(nuc, e_bins, params)
+        rn.convert_distro()
+        out = rn.inelastic(np.asarray(E, dtype=float))[0]
+        rn.close()
+        return out
+    check_against_rest_vectors(lambda sab, eb, order, E, parts: oracle.sab_calc(sab, eb, order, E, parts=parts),
+                               inelastic_of, lambda x, y, tk, tol: oracle.thin_grid(x, y, tk, tol)[0],
+                               oracle.apply_tol_scatt)
+    # the generator reproduces the committed file
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mk_rest", os.path.join(root, "scripts", "make_walk_golden_rest.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    v = np.load(os.path.join(root, "tests", "golden", "walk_vectors_rest.npz"))
+    fresh = mk.build()
+    assert set(fresh) == set(v.files)
+    for k in v.files:
+        assert np.allclose(fresh[k], v[k], rtol=1e-13, atol=1e-300), k

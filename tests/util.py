@@ -149,3 +149,46 @@ def check_library_against_oracle(n_check):
             rn.close()
         out["parity_vs_oracle"] = worst
     return keep
+
+
+def check_against_rest_vectors(sab_calc, inelastic_of, thin_grid, apply_tol):
+    """An implementation (the oracle on the CPU, the CUDA path on the GPU) against tests/golden/walk_vectors_rest.npz: the
+    committed results of the independent numpy evaluations of tests/walks.py (scripts/make_walk_golden_rest.py).
+      sab_calc(sab, e_bins, order, E, parts) -> out | (out, el, inel);  inelastic_of(nuc, e_bins, params, E) -> [NE][G][L]
+      thin_grid(x, y, tokeep, tol) -> kept indices;  apply_tol(d, tol) -> array"""
+    import os
+
+    from tests import walks
+    v = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "walk_vectors_rest.npz"))
+    for mode in ("equal", "skewed"):
+        sab, e_bins, E = walks.sab_discrete_case(mode)
+        assert np.array_equal(E, v[f"sab_disc_{mode}_Ein"])
+        assert np.allclose(sab_calc(sab, e_bins, 5, E, False), v[f"sab_disc_{mode}"], rtol=1e-11, atol=1e-13), mode
+    for elastic in ("coherent", "incoherent"):
+        sab, e_bins, E = walks.sab_elastic_case(elastic)
+        out, el, inel = sab_calc(sab, e_bins, 5, E, True)
+        ref, sig = v[f"sab_el_{elastic}"], v[f"sab_el_{elastic}_sig"]
+        for i in range(len(E) - 1):
+            assert np.allclose(el[i], ref[i], rtol=1e-11, atol=1e-13 * sig[i]), (elastic, i)
+            tot = el[i] + inel[i]
+            assert np.allclose(out[i], tot / tot[:, 0].sum(), rtol=1e-12, atol=1e-15)
+    sab, e_bins, E = walks.sab_continuous_case()
+    out, el, inel = sab_calc(sab, e_bins, 5, E, True)
+    assert np.allclose(inel[:-1], v["sab_cont_inel"][:-1], rtol=1e-10, atol=1e-12 * np.max(sab.inelastic_sigma))
+    assert np.allclose(out, v["sab_cont"], rtol=1e-10, atol=1e-13)
+    nuc, e_bins, params, spec, Ein = walks.law9_case()
+    m = inelastic_of(nuc, e_bins, params, Ein)
+    p = v["law9_p0"]
+    assert np.allclose(m[:, :, 0], p, rtol=1e-9, atol=1e-13)
+    nz = p > 1e-12
+    assert np.allclose((m[:, :, 1] / np.where(nz, m[:, :, 0], 1.0))[nz], walks.LAW9_B / 3.0, rtol=1e-8)
+    assert np.all(np.abs(m[:, :, 2:][nz] / m[:, :, :1][nz]) < 1e-8)
+    nuc, e_bins, params, Ein = walks.file6_lab_case()
+    m = inelastic_of(nuc, e_bins, params, Ein)[0]
+    assert np.allclose(m[:, 0], v["file6_lab_p0"], rtol=0, atol=1e-12)
+    assert np.allclose(m[:, 1] / m[:, 0], float(v["file6_lab_p1_over_p0"]), rtol=1e-9) and np.all(np.abs(m[:, 2:]) < 1e-9)
+    x, y, tokeep, tol = walks.thin_case()
+    assert np.array_equal(thin_grid(x, y, tokeep, tol), v["thin_keep"])
+    d, tol = walks.tol_case()
+    got = apply_tol(d, tol)
+    assert np.allclose(got, v["tol_out"], rtol=1e-15, atol=0.0) and np.all(got[9] == 0.0)
