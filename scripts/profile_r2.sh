@@ -19,4 +19,14 @@ $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 python scripts/profile_case.py --case c4d && python scripts/profile_case.py --case c4c || exit 1
 $NCU --set full -k regex:k_sab -c 6 -o $O/r2_ncu_sab_discrete python scripts/profile_case.py --case c4d > $O/r2_ncu_c4d.log 2>&1
 $NCU --set full -k regex:k_sab -c 6 -o $O/r2_ncu_sab_continuous python scripts/profile_case.py --case c4c > $O/r2_ncu_c4c.log 2>&1
-ls -la $O/*.ncu-rep
+# the reports are large (gpurun brings back at most 64 MiB): keep their raw / source pages as CSV, drop the reports
+for r in $O/r2_ncu_*.ncu-rep; do
+  ncu -i $r --page raw --csv > ${r%.ncu-rep}.raw.csv 2>/dev/null
+done
+for r in $O/r2_ncu_file6_cm_ws_c2 $O/r2_ncu_freegas_items_c3; do
+  ncu -i $r.ncu-rep --page source --csv > $r.source.csv 2>/dev/null
+done
+cuobjdump -sass -fun '_ZN4ndpp13k_file6_cm_wsILi8EEEvNS_6NucDevEPKdNS_5UbDevEPKNS_5UbRecEPKiS3_S3_S9_iiPyPd' ndpp_b200/csrc/libndppgpu.so > $O/r2_sass_k_file6_cm_ws_8.txt 2>/dev/null
+rm -f $O/r2_ncu_*.ncu-rep
+ls -la $O | tail -30
+du -sh $O

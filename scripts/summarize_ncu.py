@@ -48,11 +48,14 @@ KEYS = [("gpu__time_duration.sum", "duration"), ("launch__registers_per_thread",
 
 
 def full(rep, out, title):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):     # `ncu -i report --page raw --csv` exported on the GPU box (the reports are too large to bring back)
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, rows = rows[0], rows[1], rows[2:]
     with open(out, "w") as f:
-        f.write(f"# {title}\n\nSource: `{rep.split('/')[-1]}` (`ncu --set full --clock-control none --import-source on`).\n")
+        f.write(f"# {title}\n\nSource: `{rep.split('/')[-1]}` (`ncu --set full --clock-control none`; scripts/profile_r2.sh).\n")
         for r in rows:
             d = dict(zip(hdr, r))
             u = dict(zip(hdr, units))
