@@ -208,7 +208,11 @@ def run_reference(args):
             "config": workload_config(nuc, e_bins, params, Ein_el, Ein_inel, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            # a step of this arm is a SAMPLE of the configuration (every k-th E_in), not the configuration: `value` is the
+            # rate on the sample, ms_per_step the sample's time; the whole configuration at this rate would take:
+            "sampled": True,
+            "ms_per_step_full_config_extrapolated": 1e3 * evals_per_step(e_bins, params, Ein_el, Ein_inel) / value}
     print(json.dumps(line))
 
 
@@ -523,6 +527,16 @@ def run_configs(ctx, peak_tflops, sample_cpu=True):
             rate, n, cnt = _cpu_rate_nuclide(nuc, e_bins, params, Eel, Einel, n_cpu, threads, counters)
             row["cpu"] = {"evals_per_s": rate, "cores": threads, "kind": "port", "sample": f"{n} evenly spread E_in per grid"}
         f = flops(cnt) if callable(flops) else flops
+        if counters and st["freegas_kernel_evals"]:
+            # the device shares kernel values between the Legendre orders of a cell: claim what it evaluated (SURVEY 8d:
+            # "a kernel that legitimately shares evaluations across l may not claim the unshared count")
+            row["reference_unshared_flops"] = f
+            f = 40.0 * st["freegas_kernel_evals"] + 35.0 * st["freegas_sab_evals"]
+            row["kernel_evals"] = int(st["freegas_kernel_evals"])
+            row["sab_evals"] = int(st["freegas_sab_evals"])
+            flop_note = ("F_E = 40 N_kernel + 35 N_sab with the evaluations the device performed (counted in the kernel; one "
+                         "kernel value serves the orders of a group); reference_unshared_flops = the same formula with the "
+                         "reference's per-order counts from the instrumented oracle on the CPU sample, scaled to the grid")
         if f:
             row["roofline"] = {"bound": "fp64", "algorithmic_flops": f, "achieved": f / (st["kernel_ms"] * 1e-3) / 1e12,
                                "peak": peak_tflops, "unit": "TFLOP/s", "frac": f / (st["kernel_ms"] * 1e-3) / 1e12 / peak_tflops,

@@ -61,7 +61,8 @@ typedef struct {
     double host_alloc_ms;    /* ... of which in device allocations (stream-ordered pool) */
     double host_sync_ms;     /* ... of which blocked on the device (count read-backs, result copies) */
     long long freegas_items; /* work items the free-gas sub-integrals were cut into (all generations) */
-    double reserved[2];
+    long long freegas_kernel_evals; /* free-gas kernel values actually evaluated (shared by the Legendre orders of a group) */
+    long long freegas_sab_evals;    /* calc_sab evaluations actually performed (find_FG_mu, once per outgoing energy) */
 } ndppgpu_stats_t;
 
 /* ---- context -------------------------------------------------------------------------------- */

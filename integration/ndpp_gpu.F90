@@ -8,7 +8,8 @@
 !     -L<repo>/ndpp_b200/csrc -lndppgpu -Wl,-rpath,<repo>/ndpp_b200/csrc
 ! INTEGRATION.md shows the three procedure bodies of src/scatt.F90 that call it.
 !
-! NOTE: the image this project is built in has no Fortran compiler, so this
+! NOTE: the image this project is built in has no Fortran compiler (gfortran,
+! flang, nvfortran, ifort, ifx, lfortran, f2c probed: all absent), so this
 ! module has been written against the reference sources by inspection and has
 ! not been compiled; the identical call sequence is exercised by the C++ twin
 ! (include/ndpp_host.hpp, tools/ndpp_calc_scatt.cpp) and the Python twin
@@ -30,6 +31,10 @@ module ndpp_gpu
   public :: ndppgpu_apply_tol, ndppgpu_thin_grid
   public :: ndppgpu_sab_create, ndppgpu_sab, ndppgpu_sab_free
   public :: ndppgpu_chi
+  public :: gpu_group, gpu_group_start, gpu_group_stop
+  public :: ndppgpu_group_init, ndppgpu_group_unique_id, ndppgpu_group_init_rank, ndppgpu_group_ctx, ndppgpu_group_finalize
+  public :: ndppgpu_group_nuclide_create, ndppgpu_group_nuclide_add_reaction, ndppgpu_group_convert_distro
+  public :: ndppgpu_group_elastic, ndppgpu_group_inelastic, ndppgpu_group_nuclide_free
 
   ! include/ndppgpu.h: ndppgpu_params  (src/global.F90:28-59)
   type, bind(C) :: ndppgpu_params
@@ -261,9 +266,139 @@ module ndpp_gpu
       integer(c_int)              :: rc
     end function ndppgpu_chi
 
+    ! ---- several GPUs (include/ndppgpu.h, "several GPUs"): the GPUs of this process work on one nuclide ----
+    ! n_devices <= 0: every GPU of the box; devices = c_null_ptr: 0 .. n-1.  One host thread per device and
+    ! ncclCommInitAll happen inside the library.
+    function ndppgpu_group_init(n_devices, devices, group) bind(C, name="ndppgpu_group_init") result(rc)
+      import :: c_int, c_ptr
+      integer(c_int), value :: n_devices
+      type(c_ptr), value    :: devices
+      type(c_ptr)           :: group
+      integer(c_int)        :: rc
+    end function ndppgpu_group_init
+
+    ! one GPU per MPI rank: rank 0 makes the 128-byte NCCL id, MPI_Bcast carries it, every rank joins
+    function ndppgpu_group_unique_id(id128) bind(C, name="ndppgpu_group_unique_id") result(rc)
+      import :: c_int, c_char
+      character(kind=c_char) :: id128(128)
+      integer(c_int)         :: rc
+    end function ndppgpu_group_unique_id
+
+    function ndppgpu_group_init_rank(device, rank, world, id128, group) &
+         bind(C, name="ndppgpu_group_init_rank") result(rc)
+      import :: c_int, c_ptr, c_char
+      integer(c_int), value  :: device, rank, world
+      character(kind=c_char) :: id128(128)
+      type(c_ptr)            :: group
+      integer(c_int)         :: rc
+    end function ndppgpu_group_init_rank
+
+    ! borrowed context of a local device (errors, statistics); 0 = the device that receives the matrices on rank 0
+    function ndppgpu_group_ctx(group, local_index) bind(C, name="ndppgpu_group_ctx") result(ctx)
+      import :: c_int, c_ptr
+      type(c_ptr), value    :: group
+      integer(c_int), value :: local_index
+      type(c_ptr)           :: ctx
+    end function ndppgpu_group_ctx
+
+    function ndppgpu_group_finalize(group) bind(C, name="ndppgpu_group_finalize") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: group
+      integer(c_int)     :: rc
+    end function ndppgpu_group_finalize
+
+    ! the nuclide replicated on every device of the group: arguments of ndppgpu_nuclide_create
+    function ndppgpu_group_nuclide_create(group, awr, kT, freegas_cutoff, n_grid, energy, &
+         elastic_xs, e_bins, n_bins, params, gnuc) &
+         bind(C, name="ndppgpu_group_nuclide_create") result(rc)
+      import :: c_int, c_ptr, c_double, ndppgpu_params
+      type(c_ptr), value         :: group
+      real(c_double), value      :: awr, kT, freegas_cutoff
+      integer(c_int), value      :: n_grid, n_bins
+      real(c_double), intent(in) :: energy(*), elastic_xs(*), e_bins(*)
+      type(ndppgpu_params), intent(in) :: params
+      type(c_ptr)                :: gnuc
+      integer(c_int)             :: rc
+    end function ndppgpu_group_nuclide_create
+
+    ! arguments of ndppgpu_nuclide_add_reaction
+    function ndppgpu_group_nuclide_add_reaction(gnuc, rxn_index, MT, Q_value, threshold, &
+         scatter_in_cm, has_angle_dist, has_energy_dist, law, multiplicity, &
+         yield_tab1, n_yield, sigma, n_sigma, p_valid_tab1, n_pvalid, &
+         adist_energy, adist_type, adist_loc, n_adist_e, adist_data, n_adist_data, &
+         edist_data, n_edist_data) &
+         bind(C, name="ndppgpu_group_nuclide_add_reaction") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value    :: gnuc
+      integer(c_int), value :: rxn_index, MT, threshold, scatter_in_cm
+      integer(c_int), value :: has_angle_dist, has_energy_dist, law, multiplicity
+      real(c_double), value :: Q_value
+      type(c_ptr), value    :: yield_tab1, sigma, p_valid_tab1
+      type(c_ptr), value    :: adist_energy, adist_type, adist_loc, adist_data, edist_data
+      integer(c_int), value :: n_yield, n_sigma, n_pvalid, n_adist_e, n_adist_data, n_edist_data
+      integer(c_int)        :: rc
+    end function ndppgpu_group_nuclide_add_reaction
+
+    function ndppgpu_group_convert_distro(gnuc) bind(C, name="ndppgpu_group_convert_distro") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: gnuc
+      integer(c_int)     :: rc
+    end function ndppgpu_group_convert_distro
+
+    ! calc_elastic_grid / calc_inelastic_grid sharded over the group; the matrices arrive on rank 0
+    function ndppgpu_group_elastic(gnuc, Ein, NE, el_mat) bind(C, name="ndppgpu_group_elastic") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value         :: gnuc
+      real(c_double), intent(in) :: Ein(*)
+      integer(c_int), value      :: NE
+      real(c_double)             :: el_mat(*)
+      integer(c_int)             :: rc
+    end function ndppgpu_group_elastic
+
+    function ndppgpu_group_inelastic(gnuc, Ein, NE, inel_mat, nuinel_mat) &
+         bind(C, name="ndppgpu_group_inelastic") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value         :: gnuc
+      real(c_double), intent(in) :: Ein(*)
+      integer(c_int), value      :: NE
+      real(c_double)             :: inel_mat(*)
+      type(c_ptr), value         :: nuinel_mat     ! c_loc(nuinel_mat) or c_null_ptr
+      integer(c_int)             :: rc
+    end function ndppgpu_group_inelastic
+
+    function ndppgpu_group_nuclide_free(gnuc) bind(C, name="ndppgpu_group_nuclide_free") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: gnuc
+      integer(c_int)     :: rc
+    end function ndppgpu_group_nuclide_free
+
   end interface
 
+  type(c_ptr), save :: gpu_group = c_null_ptr     ! the device group of this process (gpu_group_start)
+
 contains
+
+!===============================================================================
+! GPU_GROUP_START / GPU_GROUP_STOP: every GPU of the box (n_devices <= 0) or the
+! first n_devices of them work together on each nuclide.  gpu_ctx becomes the
+! context of the device that receives the assembled matrices, so that gpu_check,
+! ndppgpu_apply_tol, ndppgpu_thin_grid and ndppgpu_sab keep working unchanged.
+!===============================================================================
+
+  subroutine gpu_group_start(n_devices)
+    integer, intent(in) :: n_devices
+    integer(c_int) :: rc
+    rc = ndppgpu_group_init(int(n_devices, c_int), c_null_ptr, gpu_group)
+    if (rc == 0) gpu_ctx = ndppgpu_group_ctx(gpu_group, 0_c_int)
+    call gpu_check(rc)
+  end subroutine gpu_group_start
+
+  subroutine gpu_group_stop()
+    integer(c_int) :: rc
+    if (c_associated(gpu_group)) rc = ndppgpu_group_finalize(gpu_group)
+    gpu_group = c_null_ptr
+    gpu_ctx = c_null_ptr        ! it belonged to the group
+  end subroutine gpu_group_stop
 
 !===============================================================================
 ! GPU_START / GPU_STOP create and destroy the device context of this process.

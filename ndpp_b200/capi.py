@@ -53,7 +53,7 @@ class StatsC(C.Structure):
                 ("file6_cm_points", C.c_longlong), ("file6_lab_calls", C.c_longlong), ("freegas_tasks", C.c_longlong),
                 ("sab_columns", C.c_longlong), ("file6_cm_ms", C.c_double), ("file6_cm_launches", C.c_longlong),
                 ("host_call_ms", C.c_double), ("host_alloc_ms", C.c_double), ("host_sync_ms", C.c_double),
-                ("freegas_items", C.c_longlong), ("reserved", C.c_double * 2)]
+                ("freegas_items", C.c_longlong), ("freegas_kernel_evals", C.c_longlong), ("freegas_sab_evals", C.c_longlong)]
 
 
 class ShapeC(C.Structure):
@@ -213,7 +213,7 @@ class Context:
     def stats(self, reset=False) -> dict:
         s = StatsC()
         check(self.lib.ndppgpu_stats(self.h, C.byref(s), int(reset)), self.h)
-        return {k: getattr(s, k) for k, _ in StatsC._fields_ if k != "reserved"}
+        return {k: getattr(s, k) for k, _ in StatsC._fields_}
 
     def measure_fp64_peak(self, seconds=0.5) -> float:
         out = C.c_double(0.0)

@@ -730,7 +730,10 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                                                             (n_root + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
             const size_t warps = (size_t)max_blocks * FG_WARPS_PER_BLOCK, full = (size_t)1 << n->p.adaptive_mu_its;
             TmpBuf d_ovf, d_items, d_ival, d_roff, d_rlen, d_ops, d_pay, d_tails;
-            if (tmp_alloc(c, d_ovf, sizeof(int)) || tmp_alloc(c, d_tails, 2 * sizeof(unsigned long long))) return 1;
+            TmpBuf d_evals;
+            if (tmp_alloc(c, d_ovf, sizeof(int)) || tmp_alloc(c, d_tails, 2 * sizeof(unsigned long long)) ||
+                tmp_alloc(c, d_evals, 2 * sizeof(unsigned long long)))
+                return 1;
             bool worst_scratch = false;
             // measured on C3: 1.40e6 sub-integrals hand on 1.4e5 items at 2 levels per item (3e5 at 1 level)
             long long cap_items = std::max<long long>(n_root / 2, 1LL << 18);
@@ -748,12 +751,14 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                     return 1;
                 CK(c, cudaMemsetAsync(d_ovf.p, 0, sizeof(int), c->stream));
                 CK(c, cudaMemsetAsync(d_tails.p, 0, 2 * sizeof(unsigned long long), c->stream));
+                CK(c, cudaMemsetAsync(d_evals.p, 0, 2 * sizeof(unsigned long long), c->stream));
                 FgQueue q{};
                 q.tasks = d_tasks.as<int>(); q.n_root = n_root; q.items = d_items.as<FgItem>(); q.cap_items = cap_items;
                 q.tail = d_tails.as<unsigned long long>(); q.tok_tail = q.tail + 1;
                 q.ival = d_ival.as<double>(); q.roff = d_roff.as<long long>(); q.rlen = d_rlen.as<int>();
                 q.ops = d_ops.as<unsigned char>(); q.pay = d_pay.as<double>(); q.cap_tok = cap_tok;
                 q.split_depth = c->fg_split_depth; q.overflow = d_ovf.as<int>();
+                q.evals = d_evals.as<unsigned long long>();
                 std::vector<long long> bounds{0, n_root};   // generation g = items [bounds[g], bounds[g+1])
                 int ovf = 0;
                 for (;;) {
@@ -795,6 +800,13 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 k_fg_store<<<blocks_for(n_root * FG_LW, 256), 256, 0, c->stream>>>(q, rows, n->G, n->L, raw.as<double>());
                 if (launch_check(c, "k_fg_store")) return 1;
                 c->stats.freegas_items += bounds.back();
+                {
+                    unsigned long long ev[2] = {0, 0};
+                    CK(c, cudaMemcpyAsync(ev, d_evals.p, sizeof(ev), cudaMemcpyDeviceToHost, c->stream));
+                    CK(c, cudaStreamSynchronize(c->stream));
+                    c->stats.freegas_kernel_evals += (long long)ev[0];
+                    c->stats.freegas_sab_evals += (long long)ev[1];
+                }
                 break;
             }
             k_freegas_finish<<<blocks_for((long long)n_idx * 32, 128), 128, 0, c->stream>>>(
