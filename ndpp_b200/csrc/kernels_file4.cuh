@@ -114,7 +114,16 @@ __device__ __forceinline__ void file4_cm_warp(const NucDev& nuc, const SlotDev& 
 // calc_elastic_grid.  One warp per E_in.  Columns whose E_in is below the free-gas cutoff are
 // produced by the free-gas kernels (kernels_freegas.cuh) and skipped here; columns above the top
 // group edge are filled by k_copy_top afterwards.
-__global__ void k_elastic(NucDev nuc, const SlotDev* __restrict__ slots, const int* __restrict__ el_ids, int n_el,
+// Register budgets.  Left to itself ptxas gave k_inelastic 146 registers: one block of 8 warps per SM, 12.5 % occupancy
+// (ncu: FP64 pipe 21 %, issue slots 32 %) for a latency-bound kernel.  C2, ms of everything but the file-6 pipeline per
+// step, same box: 1 block/SM (k_elastic 3) 11.3; 2 (4) at 128 registers 7.8; 3 (5) at 80 / 96 registers 8.2; 4 (6) 9.6.
+#ifndef K4_EL_BLOCKS
+#define K4_EL_BLOCKS 4
+#endif
+#ifndef K4_INEL_BLOCKS
+#define K4_INEL_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, K4_EL_BLOCKS) k_elastic(NucDev nuc, const SlotDev* __restrict__ slots, const int* __restrict__ el_ids, int n_el,
                           const double* __restrict__ Ein, int NE, double* __restrict__ out)
 {
     const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -145,7 +154,7 @@ __global__ void k_elastic(NucDev nuc, const SlotDev* __restrict__ slots, const i
 // summation order over reactions.  File-6 slots were integrated beforehand by their own kernels
 // (kernels_file6.cuh); their per-E_in results (already scaled) are read from pre[slot].
 // Dynamic shared memory: (2 + nwarps) * G * L doubles + nwarps doubles.
-__global__ void k_inelastic(NucDev nuc, const SlotDev* __restrict__ slots, const int* __restrict__ in_ids, int n_in,
+__global__ void __launch_bounds__(256, K4_INEL_BLOCKS) k_inelastic(NucDev nuc, const SlotDev* __restrict__ slots, const int* __restrict__ in_ids, int n_in,
                             const double* const* __restrict__ pre, const double* __restrict__ Ein, int NE,
                             double* __restrict__ out, double* __restrict__ nuout)
 {
