@@ -42,7 +42,11 @@ struct Ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
     int sm_count = 148;
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
-    int fg_split_depth = 2;  // NDPPGPU_FG_SPLIT: levels of the outer recursion one work item walks (1..4); C3: 506 / 485 / 455 / 452 ms at 4 / 3 / 2 / 1
+    int fg_split_late = 0;          // NDPPGPU_FG_SPLIT_LATE: the same for generations of fewer than fg_late_items items
+    long long fg_late_items = 0;    // NDPPGPU_FG_LATE_ITEMS
+    int fg_split_depth = 0;  // NDPPGPU_FG_SPLIT: levels of the outer recursion below its node that one work item walks (0..3).
+                             // C3 293.6 K / 1200 K, kernel ms: 2 -> 317 / 231, 1 -> 275 / 218, 0 (one node per item) -> 258 / 205:
+                             // the late generations hold few, heavy items and are bound by the longest chain of inner integrals
     long long fg_queue_cap = 0;               // NDPPGPU_FG_QUEUE: first-attempt capacity of the item queue (tests)
     bool f6_legacy = false;  // NDPPGPU_F6_LEGACY=1: the one-role k_file6_cm (kept for A/B parity tests)
     // file-6 CM scratch (records, sorted flags, materialised unit-base tables): kept for the life of the context
@@ -739,8 +743,9 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             long long cap_items = std::max<long long>(n_root / 2, 1LL << 18);
             if (c->fg_queue_cap > 0) cap_items = c->fg_queue_cap;
             for (int attempt = 0;; ++attempt) {
-                const size_t capF = worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap);
-                const size_t capN = worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap);
+                // up to FG_MAX_ROOTS inner integrals are walked as one forest: the level scratch holds all their trees
+                const size_t capF = FG_MAX_ROOTS * (worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap));
+                const size_t capN = FG_MAX_ROOTS * (worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap));
                 const long long cap_tok = 4 * cap_items + 64;
                 const long long n_all = n_root + cap_items;
                 if (tmp_alloc(c, d_frames, warps * 2 * (capF / 2) * sizeof(FgPair) + sizeof(FgPair)) ||
@@ -764,6 +769,9 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 for (;;) {
                     const long long lo = bounds[bounds.size() - 2], hi = bounds.back();
                     const int blocks = (int)std::min<long long>(max_blocks, (hi - lo + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
+                    // a generation with few items is bound by its longest item, not by throughput: its items walk fewer
+                    // levels, so that the nodes an item would visit one after the other run side by side
+                    q.split_depth = (hi - lo < c->fg_late_items) ? c->fg_split_late : c->fg_split_depth;
                     CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
                     CK(c, cudaFuncSetAttribute(k_freegas_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgShared)));
                     k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
@@ -1005,7 +1013,11 @@ int ndppgpu_init(int device, void** ctx)
         e = std::getenv("NDPPGPU_FG_CAP");
         if (e && std::atoi(e) >= 2) c->fg_first_cap = std::atoi(e);
         e = std::getenv("NDPPGPU_FG_SPLIT");
-        if (e && std::atoi(e) >= 1) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
+        if (e && e[0] && std::atoi(e) >= 0) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
+        e = std::getenv("NDPPGPU_FG_SPLIT_LATE");
+        if (e && e[0] && std::atoi(e) >= 0) c->fg_split_late = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
+        e = std::getenv("NDPPGPU_FG_LATE_ITEMS");
+        if (e && e[0]) c->fg_late_items = std::atoll(e);
         e = std::getenv("NDPPGPU_FG_QUEUE");
         if (e && std::atoll(e) >= 2) c->fg_queue_cap = std::atoll(e);
     }

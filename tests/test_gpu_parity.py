@@ -441,7 +441,7 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=1000)
     Ein = Ein[[0, 450, 900]]
     outs, items = [], []
-    for split, queue in (("3", None), ("2", None), ("1", None), ("2", "512")):
+    for split, queue in (("3", None), ("2", None), ("1", None), ("0", None), ("2", "512")):
         monkeypatch.setenv("NDPPGPU_FG_SPLIT", split)
         if queue is None:
             monkeypatch.delenv("NDPPGPU_FG_QUEUE", raising=False)
@@ -455,7 +455,7 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     assert np.any(outs[0] != 0)
     for o in outs[1:]:
         assert np.array_equal(outs[0], o)
-    assert items[0] < items[1] < items[2] and items[3] == items[1]
+    assert items[0] < items[1] < items[2] < items[3] and items[4] == items[1]
 
 
 def test_unitbase_and_file6_cm_leg_heavy_target_limit(scatt, oracle):
