@@ -34,7 +34,7 @@ def test_c2_full_size_properties(c2):
     # target-at-rest elastic: a probability distribution over the groups per E_in.  The angular tables are
     # integrated by the trapezoid rule on the uniform mu grid, so the sum is 1 up to that rule's O(dmu^2) error
     p0 = el[:, :, 0]
-    assert p0.min() >= 0.0 and np.allclose(p0.sum(axis=1), 1.0, atol=2e-4)
+    assert p0.min() >= 0.0 and np.allclose(p0.sum(axis=1), 1.0, atol=1.5e-4)      # measured on B200: 1.4e-5
     # |P_l| <= P_0 for a non-negative density (|P_l(mu)| <= 1), group by group
     assert np.all(np.abs(el) <= p0[:, :, None] * (1 + 1e-9) + 1e-12)
     assert np.all(np.abs(inel) <= inel[:, :, :1] * (1 + 1e-9) + 1e-10)
@@ -49,7 +49,7 @@ def test_c2_full_size_properties(c2):
         sig[r.threshold - 1:r.threshold - 1 + len(r.sigma)] += r.sigma
     off = len(nuc.energy) - inel.shape[0]
     tot = inel[:, :, 0].sum(axis=1)
-    assert np.allclose(tot[:-1], sig[off:-1], rtol=1e-6, atol=1e-12)
+    assert np.allclose(tot[:-1], sig[off:-1], rtol=1e-14, atol=1e-14)              # measured: 6.6e-16 relative
 
 
 def test_c2_full_size_sample_against_oracle(c2, oracle):
@@ -98,8 +98,9 @@ def test_c3_full_size_properties_and_sample(scatt, oracle):
     dn = scatt.DeviceNuclide(nuc, e_bins, params)
     el = dn.elastic(Ein)
     assert el.shape == (1000, 70, 4) and np.isfinite(el).all()
-    assert np.allclose(el[:, :, 0].sum(axis=1), 1.0, atol=1e-12)       # integrate_freegas_leg normalises (:131-140)
-    assert np.all(np.abs(el) <= np.abs(el[:, :, :1]) * (1 + 1e-3) + 1e-6)   # every order has its own adaptivity (tolerances 1e-7 / 1e-8)
+    assert np.allclose(el[:, :, 0].sum(axis=1), 1.0, atol=5e-15)       # integrate_freegas_leg normalises (:131-140); measured 4.4e-16
+    # every order has its own adaptivity (tolerances 1e-7 / 1e-8): measured max(|P_l| - P0) = 2.4e-7
+    assert np.all(np.abs(el) <= np.abs(el[:, :, :1]) + 2.5e-6)
     # up-scatter exists below a few kT and has died out at the cutoff
     g_in = np.searchsorted(e_bins, Ein, side="right") - 1
     up = np.array([el[k, g_in[k] + 1:, 0].sum() for k in range(1000)])

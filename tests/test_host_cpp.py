@@ -219,3 +219,37 @@ def test_cpp_fatal_error_carries_the_reference_message(tool, tmp_path):
     r = _run(tool, tmp_path / "e.case", tmp_path / "e.res", expect_ok=False)
     assert r.returncode != 0 and r.stderr.startswith(" ERROR: ") and "binary search" in r.stderr
     assert not os.path.exists(tmp_path / "e.res")
+
+
+@pytest.mark.gpu
+def test_cpp_calc_scatt_on_a_device_group(tool, tmp_path):
+    """`ndpp_calc_scatt --devices N` = calc_scatt on every GPU of the box through ndpp_host::DeviceGroup (ndppgpu_group_*:
+    E_in dealt cyclically over the devices, NCCL gather to device 0); its matrices equal the one-device program's bit for
+    bit, with and without the library step (tolerance + thinning on the root device)."""
+    import torch
+    nuc = small_heavy()
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=7, mu_bins=2001, nuscatter=True)
+    rng = np.random.default_rng(12)
+    Ein = np.sort(np.concatenate([np.exp(rng.uniform(np.log(1e-10), np.log(19.9), 90)), [20.0, 20.01]]))
+    Ein_inel = Ein[Ein >= 0.05]
+    dump.write_nuclide_case(tmp_path / "g.case", nuc, e_bins, params.scatt_type, params.order, params.mu_bins, True,
+                            Ein, Ein_inel, params)
+    _run(tool, tmp_path / "g.case", tmp_path / "one.res")
+    n = torch.cuda.device_count()
+    r = subprocess.run([tool, str(tmp_path / "g.case"), str(tmp_path / "grp.res"), "--devices", "0"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert f" {n} devices:" in r.stdout
+    a, b = dump.read_result(tmp_path / "one.res"), dump.read_result(tmp_path / "grp.res")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    for extra, tag in ((["--device", "0"], "one"), (["--devices", "0"], "grp")):
+        r = subprocess.run([tool, str(tmp_path / "g.case"), str(tmp_path / f"{tag}2.res"), "--library",
+                            str(tmp_path / f"{tag}.lib"), "--print-tol", "1e-8", "--thin-tol", "0.002"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "one.lib", "rb").read() == open(tmp_path / "grp.lib", "rb").read()
+    r = subprocess.run([tool, str(tmp_path / "g.case"), str(tmp_path / "x.res"), "--devices", str(n + 1)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "ERROR: ndppgpu_group_init: more devices requested than the box has" in r.stderr
