@@ -218,7 +218,9 @@ int ndppgpu_test_exact_math(void *ctx, unsigned long long seed, int per_thread, 
 /* The device's sinh / cosh / expm1 / exp (csrc/libm_exact.cuh: a restatement of the algorithms of the host C library
  * the reference's Fortran calls, GNU libc 2.39 x86-64 FMA builds) at n host arguments; fn = 0 exp, 1 expm1, 2 sinh,
  * 3 cosh.  convert_file6's Law 44 (src/scattdata_header.F90:822-831) is built from these, and the parity tests compare
- * them bit for bit with the running libm. */
+ * them bit for bit with the running libm.  fn 10 .. 12: the branch-free primitives of the free-gas kernel (exp for
+ * -708 < x <= 0, sqrt, x[i] / x[i ^ 1]; n even for 12): where a primitive's range guard fails the library operation is
+ * returned, so comparing y with exp / sqrt / division tests exactly the guarded results. */
 int ndppgpu_eval_libm(void *ctx, int fn, const double *x, long long n, double *y);
 
 int ndppgpu_test_legendre(void *ctx, int n, int L, const double *xlow, const double *xhigh, const double *flow,

@@ -484,6 +484,17 @@ __global__ void k_eval_libm(int fn, const double* __restrict__ x, double* __rest
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double v = x[i];
+        if (fn >= 10) {
+            // the branch-free primitives of fg_base2 (kernels_freegas.cuh): their value where their guard holds, else
+            // the library operation they stand for -- a caller comparing with that operation sees every guarded mismatch
+            bool ok = true;
+            double r;
+            if (fn == 10) { r = fg_exp_neg(v, ok); if (!ok || v <= -708.0) r = lm::exp_(v); }
+            else if (fn == 11) { r = fg_sqrt_fast(v, ok); if (!ok) r = sqrt(v); }
+            else { const double d = x[i ^ 1LL]; r = fg_div_fast(v, d, ok); if (!ok) r = v / d; }
+            y[i] = r;
+            continue;
+        }
         y[i] = fn == 2 ? lm::sinh_(v) : fn == 3 ? lm::cosh_(v) : fn == 1 ? lm::expm1_(v) : lm::exp_(v);
     }
 }
@@ -1764,7 +1775,9 @@ int ndppgpu_eval_libm(void* ctx, int fn, const double* x, long long n, double* y
 {
     Ctx* c = (Ctx*)ctx;
     if (!c || !x || !y) return fail(c, "ndppgpu_eval_libm: null argument");
-    if (fn < 0 || fn > 3) return fail(c, "ndppgpu_eval_libm: fn must be 0 (exp), 1 (expm1), 2 (sinh) or 3 (cosh)");
+    if (fn < 0 || (fn > 3 && fn < 10) || fn > 12)
+        return fail(c, "ndppgpu_eval_libm: fn must be 0 (exp), 1 (expm1), 2 (sinh), 3 (cosh) or 10 .. 12 (free-gas primitives)");
+    if (fn == 12 && (n & 1)) return fail(c, "ndppgpu_eval_libm: fn 12 divides x[i] by x[i ^ 1]: n must be even");
     if (n <= 0) return 0;
     CK(c, cudaSetDevice(c->device));
     TmpBuf dx, dy;

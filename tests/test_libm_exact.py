@@ -112,3 +112,46 @@ def test_device_exp_expm1(chk):
         chk.libm_host_eval(FN[name], x.ctypes.data_as(dp), ref.ctypes.data_as(dp), len(x))
         got = ctx.eval_libm(FN[name], x)
         assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
+
+
+@pytest.mark.gpu
+def test_device_free_gas_primitives_carry_the_library_bits(chk):
+    """The branch-free division, square root and exp of the free-gas kernel's two-point evaluation (fg_div_fast,
+    fg_sqrt_fast, fg_exp_neg in csrc/kernels_freegas.cuh) against `/`, sqrt and the host libm's exp: >= 1e8 arguments
+    each over the magnitudes the kernel meets (and far beyond), bit for bit wherever their range guard holds (elsewhere
+    the device returns the library operation itself, ndppgpu.h: ndppgpu_eval_libm fn 10-12)."""
+    from ndpp_b200 import scatt
+    ctx = scatt.default_context()
+    rng = np.random.default_rng(1012)
+    dp = C.POINTER(C.c_double)
+    n = 10_000_000
+    totals = [0, 0, 0]
+    for rep in range(10):
+        # exp on (-708, 0]: uniform, and log-uniform magnitudes down to the tiny branch
+        x = -rng.uniform(0.0, 708.0, n) if rep < 6 else -(10.0 ** rng.uniform(-20.0, 2.85, n))
+        x = np.maximum(x, -707.999)
+        ref = np.empty_like(x)
+        chk.libm_host_eval(FN["exp"], x.ctypes.data_as(dp), ref.ctypes.data_as(dp), n)
+        got = ctx.eval_libm(10, x)
+        bad = np.nonzero(got.view(np.uint64) != ref.view(np.uint64))[0]
+        assert bad.size == 0, f"exp: {bad.size} of {n}, e.g. x = {x[bad[0]]!r}: {got[bad[0]]!r} vs {ref[bad[0]]!r}"
+        totals[0] += n
+        # sqrt: mantissas uniform, exponents over the whole range (and the kernel's 4 pi alpha in [1e-5, 1e6])
+        x = rng.uniform(1.0, 4.0, n) * (2.0 ** rng.integers(-1020, 1020, n) if rep % 2 else 10.0 ** rng.uniform(-6, 7, n))
+        got = ctx.eval_libm(11, x)
+        ref = np.sqrt(x)
+        bad = np.nonzero(got.view(np.uint64) != ref.view(np.uint64))[0]
+        assert bad.size == 0, f"sqrt: {bad.size} of {n}, e.g. x = {x[bad[0]]!r}: {got[bad[0]]!r} vs {ref[bad[0]]!r}"
+        totals[1] += n
+        # division x[i] / x[i ^ 1]
+        e = rng.uniform(-30, 30, n) if rep % 2 else rng.uniform(-290, 290, n)
+        x = rng.uniform(1.0, 10.0, n) * 10.0 ** e * np.where(rng.random(n) < 0.3, -1.0, 1.0)
+        x[::1000] = 0.0
+        with np.errstate(all="ignore"):
+            ref = x / x.reshape(-1, 2)[:, ::-1].reshape(-1)
+        got = ctx.eval_libm(12, x)
+        same = (got.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(got) & np.isnan(ref))
+        bad = np.nonzero(~same)[0]
+        assert bad.size == 0, f"div: {bad.size} of {n}, e.g. {x[bad[0]]!r} / {x[bad[0] ^ 1]!r}: {got[bad[0]]!r} vs {ref[bad[0]]!r}"
+        totals[2] += n
+    assert min(totals) >= 100_000_000
