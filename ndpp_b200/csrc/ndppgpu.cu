@@ -42,8 +42,6 @@ struct Ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
     int sm_count = 148;
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
-    int fg_split_late = 0;          // NDPPGPU_FG_SPLIT_LATE: the same for generations of fewer than fg_late_items items
-    long long fg_late_items = 0;    // NDPPGPU_FG_LATE_ITEMS
     int fg_split_depth = 0;  // NDPPGPU_FG_SPLIT: levels of the outer recursion below its node that one work item walks (0..3).
                              // C3 293.6 K / 1200 K, kernel ms: 2 -> 317 / 231, 1 -> 275 / 218, 0 (one node per item) -> 258 / 205:
                              // the late generations hold few, heavy items and are bound by the longest chain of inner integrals
@@ -114,6 +112,8 @@ struct TmpBuf {
     TmpBuf& operator=(const TmpBuf&) = delete;
     template <class T> T* as() const { return (T*)p; }
 };
+
+static inline void* align_up(void* p, size_t a) { return (void*)(((uintptr_t)p + a - 1) / a * a); }
 
 int tmp_alloc(Ctx* c, TmpBuf& b, size_t bytes)
 {
@@ -755,12 +755,14 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
             if (c->fg_queue_cap > 0) cap_items = c->fg_queue_cap;
             for (int attempt = 0;; ++attempt) {
                 // up to FG_MAX_ROOTS inner integrals are walked as one forest: the level scratch holds all their trees
-                const size_t capF = FG_MAX_ROOTS * (worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap));
-                const size_t capN = FG_MAX_ROOTS * (worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap));
+                // (multiples of 4: a warp's two frontier buffers and its node values start on 128-byte lines, which
+                // the kernel discards from the L2 once they are dead)
+                const size_t capF = (FG_MAX_ROOTS * (worst_scratch ? full : std::min<size_t>(full, (size_t)c->fg_first_cap)) + 3) & ~(size_t)3;
+                const size_t capN = (FG_MAX_ROOTS * (worst_scratch ? 2 * full : std::min<size_t>(2 * full, 8 * (size_t)c->fg_first_cap)) + 3) & ~(size_t)3;
                 const long long cap_tok = 4 * cap_items + 64;
                 const long long n_all = n_root + cap_items;
-                if (tmp_alloc(c, d_frames, warps * 2 * (capF / 2) * sizeof(FgPair) + sizeof(FgPair)) ||
-                    tmp_alloc(c, d_nvals, warps * capN * FG_LW * sizeof(double)) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
+                if (tmp_alloc(c, d_frames, warps * 2 * (capF / 2) * sizeof(FgPair) + sizeof(FgPair) + 128) ||
+                    tmp_alloc(c, d_nvals, warps * capN * FG_LW * sizeof(double) + 128) || tmp_alloc(c, d_nchilds, warps * capN * sizeof(int)) ||
                     tmp_alloc(c, d_items, (size_t)cap_items * sizeof(FgItem)) || tmp_alloc(c, d_ival, (size_t)n_all * FG_LW * sizeof(double)) ||
                     tmp_alloc(c, d_roff, (size_t)n_all * sizeof(long long)) || tmp_alloc(c, d_rlen, (size_t)n_all * sizeof(int)) ||
                     tmp_alloc(c, d_ops, (size_t)cap_tok) || tmp_alloc(c, d_pay, (size_t)cap_tok * FG_LW * sizeof(double)))
@@ -775,31 +777,25 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 q.ops = d_ops.as<unsigned char>(); q.pay = d_pay.as<double>(); q.cap_tok = cap_tok;
                 q.split_depth = c->fg_split_depth; q.overflow = d_ovf.as<int>();
                 q.evals = d_evals.as<unsigned long long>();
-                std::vector<long long> bounds{0, n_root};   // generation g = items [bounds[g], bounds[g+1])
+                // one launch: later items are taken as they are appended (kernels_freegas.cuh)
+                TmpBuf d_ready, d_done;
+                if (tmp_alloc(c, d_ready, (size_t)cap_items * sizeof(int)) || tmp_alloc(c, d_done, 16)) return 1;
+                CK(c, cudaMemsetAsync(d_ready.p, 0, (size_t)cap_items * sizeof(int), c->stream));
+                CK(c, cudaMemsetAsync(d_done.p, 0, 16, c->stream));
+                q.ready = d_ready.as<int>(); q.completed = d_done.as<unsigned long long>(); q.done = d_done.as<int>() + 2;
                 int ovf = 0;
-                for (;;) {
-                    const long long lo = bounds[bounds.size() - 2], hi = bounds.back();
-                    const int blocks = (int)std::min<long long>(max_blocks, (hi - lo + FG_WARPS_PER_BLOCK - 1) / FG_WARPS_PER_BLOCK);
-                    // a generation with few items is bound by its longest item, not by throughput: its items walk fewer
-                    // levels, so that the nodes an item would visit one after the other run side by side
-                    q.split_depth = (hi - lo < c->fg_late_items) ? c->fg_split_late : c->fg_split_depth;
+                unsigned long long tails[2] = {0, 0};
+                {
                     CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
                     CK(c, cudaFuncSetAttribute(k_freegas_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgShared)));
-                    k_freegas_items<<<blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
-                        n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q, lo, hi,
-                        d_counter.as<unsigned long long>(), d_frames.as<FgPair>(), d_nvals.as<double>(), d_nchilds.as<int>(),
-                        (int)capF, (int)capN, d_ovf.as<int>());
+                    k_freegas_items<<<max_blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
+                        n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q,
+                        d_counter.as<unsigned long long>(), (FgPair*)align_up(d_frames.p, 128), (double*)align_up(d_nvals.p, 128),
+                        d_nchilds.as<int>(), (int)capF, (int)capN, d_ovf.as<int>());
                     if (launch_check(c, "k_freegas_items")) return 1;
-                    unsigned long long tails[2] = {0, 0};
                     CK(c, cudaMemcpyAsync(tails, d_tails.p, sizeof(tails), cudaMemcpyDeviceToHost, c->stream));
                     CK(c, cudaMemcpyAsync(&ovf, d_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                     CK(c, cudaStreamSynchronize(c->stream));
-                    if (ovf) break;
-                    const long long new_hi = n_root + (long long)tails[0];
-                    if (new_hi == hi) break;
-                    if (bounds.size() > (size_t)n->p.adaptive_eout_its + 3)
-                        return fail(c, "ndppgpu: free-gas item generations did not terminate");
-                    bounds.push_back(new_hi);
                 }
                 if (ovf) {
                     if (attempt >= 6) return fail(c, "ndppgpu: free-gas recursion outgrew its scratch");
@@ -810,15 +806,17 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                     if (ovf & 2) cap_items *= 4;
                     continue;
                 }
-                // items that referred to later generations: evaluate their programs, last generation first
-                for (int g = (int)bounds.size() - 3; g >= 0; --g) {
-                    const long long lo = bounds[g], hi = bounds[g + 1];
-                    k_fg_combine<<<blocks_for((hi - lo) * FG_LW, 256), 256, 0, c->stream>>>(q, lo, hi);
-                    if (launch_check(c, "k_fg_combine")) return 1;
+                // items that referred to later ones: evaluate their programs, deepest level of the recursion first
+                {
+                    const long long n_used = n_root + (long long)tails[0];
+                    for (int b = 0; b <= n->p.adaptive_eout_its; ++b) {
+                        k_fg_combine<<<blocks_for(n_used * FG_LW, 256), 256, 0, c->stream>>>(q, n_used, b, n->p.adaptive_eout_its);
+                        if (launch_check(c, "k_fg_combine")) return 1;
+                    }
                 }
                 k_fg_store<<<blocks_for(n_root * FG_LW, 256), 256, 0, c->stream>>>(q, rows, n->G, n->L, raw.as<double>());
                 if (launch_check(c, "k_fg_store")) return 1;
-                c->stats.freegas_items += bounds.back();
+                c->stats.freegas_items += n_root + (long long)tails[0];
                 {
                     unsigned long long ev[2] = {0, 0};
                     CK(c, cudaMemcpyAsync(ev, d_evals.p, sizeof(ev), cudaMemcpyDeviceToHost, c->stream));
@@ -1025,10 +1023,6 @@ int ndppgpu_init(int device, void** ctx)
         if (e && std::atoi(e) >= 2) c->fg_first_cap = std::atoi(e);
         e = std::getenv("NDPPGPU_FG_SPLIT");
         if (e && e[0] && std::atoi(e) >= 0) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
-        e = std::getenv("NDPPGPU_FG_SPLIT_LATE");
-        if (e && e[0] && std::atoi(e) >= 0) c->fg_split_late = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
-        e = std::getenv("NDPPGPU_FG_LATE_ITEMS");
-        if (e && e[0]) c->fg_late_items = std::atoll(e);
         e = std::getenv("NDPPGPU_FG_QUEUE");
         if (e && std::atoll(e) >= 2) c->fg_queue_cap = std::atoll(e);
     }
