@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NDPPGPU_ABI_VERSION 2
+#define NDPPGPU_ABI_VERSION 3
 
 /* run-time integration parameters: src/global.F90:28-59, defaults src/constants.F90:69-100 */
 typedef struct {
@@ -128,6 +128,18 @@ int ndppgpu_nuclide_set_table(void *nuc, int slot, int iE, const double *distro)
 /* ScattData%interp_distro (src/scattdata_header.F90:391-499) of one slot at NE incoming energies:
  * distro[NE][G][L], scaled by sigma_s * p_valid for non-elastic reactions exactly as the reference. */
 int ndppgpu_interp_distro(void *nuc, int slot, const double *Ein, int NE, double *distro);
+/* create_Ein_grid (src/scatt.F90:166-236: combine_Eins :246, add_elastic_Eins :311, add_one_more_point :426,
+ * add_inelastic_Eins :456) with calc_scatt's inel_thresh and cutoff (:89-120), on the device, after
+ * ndppgpu_convert_distro as in the reference (:107-139).  extend_pts / inel_extend_pts = EXTEND_PTS / INEL_EXTEND_PTS
+ * (src/constants.F90:85-86: 50 / 30).  The grids stay on the device; *n_el / *n_inel receive their lengths (*n_inel = 0
+ * for a nuclide with elastic scattering only: Ein_inel stays unallocated in the reference).  The points the reference
+ * places with log / exp carry the bits of the host's C library (csrc/libm_exact.cuh).  *status (nullable): bit 1 a
+ * critical energy of add_inelastic_Eins was NaN and its points were left out (the reference's merge would be
+ * poisoned), bit 2 an input array held a repeated value (dropped here; the reference's merge keeps some). */
+int ndppgpu_nuclide_create_ein_grid(void *nuc, int extend_pts, int inel_extend_pts, int *n_el, int *n_inel, int *status);
+/* which = 0: Ein_el, 1: Ein_inel.  Ein (nullable): host array of the length returned above; d_Ein (nullable) receives
+ * the device pointer (valid until the next create_ein_grid / nuclide_free) for ndppgpu_elastic_dev / _inelastic_dev. */
+int ndppgpu_nuclide_ein_grid(void *nuc, int which, double *Ein, const double **d_Ein);
 /* ScattData%clear for all slots (src/scatt.F90:153-155) */
 int ndppgpu_nuclide_free(void *nuc);
 
@@ -150,6 +162,11 @@ int ndppgpu_sab(void *sab, const double *e_bins, int n_bins, int scatt_type, int
                 double *scatt_mat, double *el_out, double *inel_out);
 int ndppgpu_sab_dev(void *sab, const double *e_bins, int n_bins, int scatt_type, int order, const double *d_Ein,
                     int NE, double *d_scatt_mat);
+/* sab_egrid (src/sab.F90:460-568) on the device: merged incoming grids + group structure + the incoming energies at
+ * which an outgoing energy crosses a group edge, cut at the tables' top, extend_pts (EXTEND_PTS) points inside every
+ * interval unless sab_epts_per_bin (SAB_EPTS_PER_BIN, src/global.F90) is 0.  *n = length; ndppgpu_sab_ein_grid as above. */
+int ndppgpu_sab_egrid(void *sab, const double *e_bins, int n_bins, int sab_epts_per_bin, int extend_pts, int *n, int *status);
+int ndppgpu_sab_ein_grid(void *sab, double *Ein, const double **d_Ein);
 int ndppgpu_sab_free(void *sab);
 
 /* ---- leaf check of the device Legendre helpers: integrals[n][L] = calc_int_pn_tablelin(L, xlow, xhigh,

@@ -27,6 +27,7 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
            "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
            "ndppgpu_inelastic_thinned", "ndppgpu_chi", "ndppgpu_eval_libm",
+           "ndppgpu_nuclide_create_ein_grid", "ndppgpu_nuclide_ein_grid", "ndppgpu_sab_egrid", "ndppgpu_sab_ein_grid",
            "ndppgpu_group_init", "ndppgpu_group_unique_id", "ndppgpu_group_init_rank", "ndppgpu_group_info",
            "ndppgpu_group_ctx", "ndppgpu_group_gathered_bytes", "ndppgpu_group_finalize",
            "ndppgpu_group_nuclide_create", "ndppgpu_group_nuclide_add_reaction", "ndppgpu_group_convert_distro",
@@ -110,6 +111,10 @@ def load() -> C.CDLL:
     L.ndppgpu_nuclide_slot_row_np.argtypes = [vp, i, i]
     L.ndppgpu_nuclide_get_table.argtypes = [vp, i, i, c_dp, c_dp, c_dp, c_dp, c_ip]
     L.ndppgpu_nuclide_free.argtypes = [vp]
+    L.ndppgpu_nuclide_create_ein_grid.argtypes = [vp, i, i, c_ip, c_ip, c_ip]
+    L.ndppgpu_nuclide_ein_grid.argtypes = [vp, i, c_dp, C.POINTER(vp)]
+    L.ndppgpu_sab_egrid.argtypes = [vp, c_dp, i, i, i, c_ip, c_ip]
+    L.ndppgpu_sab_ein_grid.argtypes = [vp, c_dp, C.POINTER(vp)]
     L.ndppgpu_sab_create.argtypes = [vp, d, d, d, d, i, i, i, i, c_dp, c_dp, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp, i,
                                      i, i, c_dp, c_dp, c_dp, C.POINTER(vp)]
     L.ndppgpu_sab.argtypes = [vp, c_dp, i, i, i, c_dp, i, c_dp, c_dp, c_dp]

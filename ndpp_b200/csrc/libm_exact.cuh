@@ -51,6 +51,23 @@ NDPP_LM_HD uint64_t tab(int i)
 #endif
 }
 
+#ifdef __CUDACC__
+__device__ const uint64_t d_log_tab[274] = {
+#include "log_table.inc"
+};
+#endif
+static const uint64_t h_log_tab[274] = {
+#include "log_table.inc"
+};
+NDPP_LM_HD uint64_t ltab(int i)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(&d_log_tab[i]);
+#else
+    return h_log_tab[i];
+#endif
+}
+
 NDPP_LM_HD uint64_t as_u64(double x)
 {
 #ifdef __CUDA_ARCH__
@@ -249,6 +266,60 @@ NDPP_LM_HD double cosh_(double x)
     }
     if (ix >= 0x7ff00000u) return x * x;
     return 1.0e300 * 1.0e300;
+}
+
+// log(x): sysdeps/ieee754/dbl-64/e_log.c (table-driven, N = 128: z = x / 2^k in [0x1.6p-1, 0x1.6p0), c near the centre
+// of z's sub-interval, r = z/c - 1 by one fma with the table's 1/c, degree-5 polynomial A; inside [1 - 2^-4, 1 + 0x1.09p-4)
+// the degree-11 polynomial B with a double-double head).  FMA copy: the contractions below are those of the function the
+// ifunc resolver picks on this class of CPU, read off its instruction stream.  Constants: log_table.inc
+// (scripts/gen_log_table.py).  The incoming-energy grid builders (src/scatt.F90:311-536, src/sab.F90:548-566) place their
+// points with log and exp of the host libm.
+NDPP_LM_HD double log_(double x)
+{
+    uint64_t ix = as_u64(x);
+    const double Ln2hi = as_f64(ltab(0)), Ln2lo = as_f64(ltab(1));
+    if (ix - 0x3fee000000000000ull < 0x0003090000000000ull) {            // 1 - 2^-4 <= x < 1 + 0x1.09p-4
+        if (ix == 0x3ff0000000000000ull) return 0.0;
+        const double r = x - 1.0;
+        const double B0 = as_f64(ltab(7)), B1 = as_f64(ltab(8)), B2 = as_f64(ltab(9)), B3 = as_f64(ltab(10)),
+                     B4 = as_f64(ltab(11)), B5 = as_f64(ltab(12)), B6 = as_f64(ltab(13)), B7 = as_f64(ltab(14)),
+                     B8 = as_f64(ltab(15)), B9 = as_f64(ltab(16)), B10 = as_f64(ltab(17));
+        const double r2 = r * r, r3 = r * r2;
+        const double p123 = fma_(r2, B3, fma_(r, B2, B1));
+        const double p456 = fma_(r2, B6, fma_(r, B5, B4));
+        double p = fma_(r3, B10, fma_(r2, B9, fma_(r, B8, B7)));
+        p = fma_(p, r3, p456);
+        p = fma_(p, r3, p123);
+        const double rw = fma_(r, 0x1p27, r);                             // r + r * 2^27
+        const double rhi = fma_(-0x1p27, r, rw);
+        const double rlo = r - rhi;
+        const double rhi2 = rhi * rhi;
+        const double hi = fma_(rhi2, B0, r);
+        double lo = fma_(rhi2, B0, r - hi);
+        lo = fma_(B0 * rlo, rhi + r, lo);
+        return fma_(p, r3, lo) + hi;
+    }
+    const uint32_t top = (uint32_t)(ix >> 48);
+    if (top - 0x0010u >= 0x7ff0u - 0x0010u) {
+        if (ix * 2 == 0) return as_f64(0xfff0000000000000ull);             // log(+-0) = -inf
+        if (ix == 0x7ff0000000000000ull) return x;                        // log(inf) = inf
+        if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return as_f64(0x7ff8000000000000ull) + (x - x);   // x < 0 or NaN -> NaN
+        ix = as_u64(x * 0x1p52) - (52ull << 52);                          // subnormal: normalise
+    }
+    const uint64_t tmp = ix - 0x3fe6000000000000ull;
+    const int i = (int)((tmp >> 45) & 127);
+    const int k = (int)((int64_t)tmp >> 52);
+    const double z = as_f64(ix - (tmp & 0xfff0000000000000ull));
+    const double invc = as_f64(ltab(18 + 2 * i)), logc = as_f64(ltab(19 + 2 * i));
+    const double A0 = as_f64(ltab(2)), A1 = as_f64(ltab(3)), A2 = as_f64(ltab(4)), A3 = as_f64(ltab(5)), A4 = as_f64(ltab(6));
+    const double kd = (double)k;
+    const double r = fma_(z, invc, -1.0);
+    const double w = fma_(kd, Ln2hi, logc);
+    const double hi = w + r;
+    const double lo = fma_(kd, Ln2lo, (w - hi) + r);
+    const double r2 = r * r;
+    const double q = fma_(fma_(r, A4, A3), r2, fma_(r, A2, A1));
+    return fma_(r * r2, q, fma_(r2, A0, lo)) + hi;
 }
 
 }  // namespace lm

@@ -27,6 +27,7 @@
 #include "kernels_post.cuh"
 #include "kernels_sab.cuh"
 #include "kernels_chi.cuh"
+#include "kernels_egrid.cuh"
 
 using namespace ndpp;
 
@@ -221,6 +222,8 @@ struct Nuclide {
     std::vector<int> el_ids, in_ids;
     int L = 0, G = 0;
     bool converted = false;
+    DevBuf d_ein_el, d_ein_inel;   // the grids of ndppgpu_nuclide_create_ein_grid
+    int n_ein_el = 0, n_ein_inel = 0;
 };
 
 bool is_valid_scatter(int MT)  // src/scattdata_header.F90:1502-1515
@@ -495,7 +498,7 @@ __global__ void k_eval_libm(int fn, const double* __restrict__ x, double* __rest
             y[i] = r;
             continue;
         }
-        y[i] = fn == 2 ? lm::sinh_(v) : fn == 3 ? lm::cosh_(v) : fn == 1 ? lm::expm1_(v) : lm::exp_(v);
+        y[i] = fn == 4 ? lm::log_(v) : fn == 2 ? lm::sinh_(v) : fn == 3 ? lm::cosh_(v) : fn == 1 ? lm::expm1_(v) : lm::exp_(v);
     }
 }
 
@@ -944,6 +947,9 @@ struct Sab {
     std::vector<double> wgt;
     bool wgt_error = false;
     DevBuf e_in, sigma, e_out, mu, cont_n, cont_off, cont_e, cont_pdf, cont_mu, el_e_in, el_P, el_mu, d_wgt;
+    double e_in_first = 0.0, e_in_last = 0.0, el_in_first = 0.0, el_in_last = 0.0;   // host copies for ndppgpu_sab_egrid
+    DevBuf d_ein;                  // the grid of ndppgpu_sab_egrid
+    int n_ein = 0;
 };
 
 int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order, const double* d_Ein, int NE,
@@ -990,6 +996,224 @@ int sab_dev(Sab* s, const double* e_bins, int n_bins, int scatt_type, int order,
     CK(c, cudaStreamSynchronize(c->stream));  // e_bins is caller-owned pageable memory
     c->stats.sab_columns += NE;
     c->stats.moment_evals += (long long)NE * GL;
+    return 0;
+}
+
+
+// ---- incoming-energy grids (kernels_egrid.cuh) -----------------------------------------------------------------------
+struct EgWork {
+    TmpBuf cand, sorted, uniq, count, n_unique, res, status, cub_tmp;
+    EgOut out{};
+    long long cap = 0;
+};
+
+int eg_begin(Ctx* c, EgWork& w, long long cap)
+{
+    w.cap = cap;
+    if (tmp_alloc(c, w.cand, (size_t)cap * sizeof(double)) || tmp_alloc(c, w.sorted, (size_t)cap * sizeof(double)) ||
+        tmp_alloc(c, w.uniq, (size_t)(cap + 2) * sizeof(double)) || tmp_alloc(c, w.count, sizeof(unsigned long long)) ||
+        tmp_alloc(c, w.n_unique, sizeof(int)) || tmp_alloc(c, w.res, 2 * sizeof(int)) || tmp_alloc(c, w.status, sizeof(int)))
+        return 1;
+    CK(c, cudaMemsetAsync(w.count.p, 0, sizeof(unsigned long long), c->stream));
+    CK(c, cudaMemsetAsync(w.res.p, 0, 2 * sizeof(int), c->stream));
+    CK(c, cudaMemsetAsync(w.status.p, 0, sizeof(int), c->stream));
+    w.out.cand = w.cand.as<double>(); w.out.count = w.count.as<unsigned long long>(); w.out.cap = cap;
+    w.out.status = w.status.as<int>();
+    return 0;
+}
+
+int eg_copy(Ctx* c, EgWork& w, const double* d_src, int n, int zero_to_min)
+{
+    if (n <= 0) return 0;
+    k_eg_copy<<<blocks_for(n, 256), 256, 0, c->stream>>>(d_src, n, w.out, zero_to_min);
+    return launch_check(c, "k_eg_copy");
+}
+
+// candidates -> ascending, repeats dropped, in w.uniq; *w.n_unique = their number
+int eg_sort_unique(Ctx* c, EgWork& w)
+{
+    unsigned long long cnt = 0;
+    CK(c, cudaMemcpyAsync(&cnt, w.count.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (cnt > (unsigned long long)w.cap) return fail(c, "ndppgpu: incoming-energy grid: more candidate points than the bound");
+    if (cnt == 0) return fail(c, "ndppgpu: incoming-energy grid: no points");
+    const int n = (int)cnt;
+    size_t b1 = 0, b2 = 0;
+    CK(c, cub::DeviceRadixSort::SortKeys(nullptr, b1, w.cand.as<double>(), w.sorted.as<double>(), n, 0, 64, c->stream));
+    CK(c, cub::DeviceSelect::Unique(nullptr, b2, w.sorted.as<double>(), w.uniq.as<double>(), w.n_unique.as<int>(), n, c->stream));
+    if (tmp_alloc(c, w.cub_tmp, std::max(b1, b2))) return 1;
+    b1 = b2 = w.cub_tmp.bytes;
+    CK(c, cub::DeviceRadixSort::SortKeys(w.cub_tmp.p, b1, w.cand.as<double>(), w.sorted.as<double>(), n, 0, 64, c->stream));
+    CK(c, cub::DeviceSelect::Unique(w.cub_tmp.p, b2, w.sorted.as<double>(), w.uniq.as<double>(), w.n_unique.as<int>(), n, c->stream));
+    c->stats.launches += 2;
+    return 0;
+}
+
+int eg_keep(Ctx* c, EgWork& w, DevBuf& dst, int* n_out, int* status_acc)
+{
+    int res[2] = {0, 0}, st = 0;
+    CK(c, cudaMemcpyAsync(res, w.res.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&st, w.status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *status_acc |= st;
+    if (st & EG_ST_RANGE) return fail(c, "Value outside of array during binary search");   // src/search.F90:36-38
+    if (st & EG_ST_OVERFLOW) return fail(c, "ndppgpu: incoming-energy grid: candidate buffer too small");
+    *n_out = res[0];
+    if (dev_alloc(c, dst, (size_t)res[0] * sizeof(double))) return 1;
+    CK(c, cudaMemcpyAsync(dst.p, w.uniq.p, (size_t)res[0] * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+// 1-based binary_search of the reference on a host array (the cut of an input array at E_bins(size): a launch bound)
+int host_search1(const std::vector<double>& a, double val)
+{
+    int L = 1, R = (int)a.size();
+    while (R - L > 1) { const int mid = L + (R - L) / 2; if (val >= a[mid - 1]) L = mid; else R = mid; }
+    return L;
+}
+
+int create_ein_grid(Nuclide* n, int extend_pts, int inel_extend_pts, int* n_el, int* n_inel, int* status)
+{
+    Ctx* c = n->ctx;
+    if (require_converted(n)) return 1;
+    if (extend_pts < 1 || inel_extend_pts < 1) return fail(c, "ndppgpu_nuclide_create_ein_grid: EXTEND_PTS / INEL_EXTEND_PTS must be positive");
+    Timed tm(c, &c->pending_all);
+    const int nb = (int)n->e_bins.size(), ng = (int)n->energy.size();
+    const double top = n->e_bins.back();
+    int st_acc = 0;
+    // calc_scatt's preamble (src/scatt.F90:89-120): inelastic threshold, free-gas cutoff of the elastic channel
+    double thresh = top, cutoff = 0.0;
+    bool only_el = true, all_zero = (n->energy[0] == 0.0) && (n->e_bins[0] == 0.0);
+    struct Src { const double* d; int n; };
+    std::vector<Src> srcs;
+    std::vector<double> negQ;
+    long long cap = 0;
+    {
+        const int iEmax = top >= n->energy.back() ? ng : host_search1(n->energy, top);
+        srcs.push_back({n->d_energy.as<double>(), iEmax});
+        srcs.push_back({n->d_e_bins.as<double>(), nb});
+    }
+    for (auto& sp : n->slots) {
+        Slot* s = sp.get();
+        if (!s->is_init) continue;
+        if (s->rxn->MT == MT_ELASTIC) cutoff = n->freegas_cutoff;
+        else {
+            only_el = false;
+            if (s->rxn->threshold < 1 || s->rxn->threshold > ng) return fail(c, "ndppgpu: reaction threshold outside the nuclide grid");
+            thresh = std::min(thresh, n->energy[s->rxn->threshold - 1]);
+        }
+        if (-s->rxn->Q != 0.0) negQ.push_back(-s->rxn->Q);
+        if (n->e_bins[0] >= s->e_grid.back() || top <= s->e_grid[0]) continue;       // combine_Eins :275-278
+        const int iEmax = top >= s->e_grid.back() ? (int)s->e_grid.size() : host_search1(s->e_grid, top);
+        srcs.push_back({s->dev.e_grid, iEmax});
+        if (s->e_grid[0] != 0.0) all_zero = false;
+    }
+    for (auto& r : srcs) cap += r.n;
+    cap += 2LL * (nb - 1) * extend_pts + 8;
+    // a zero survives the chain of merges only when every merged array starts with zero and no extension point exists
+    const int zero_to_min = !(all_zero && nb <= 2 && cutoff == 0.0);
+    {
+        EgWork w;
+        if (eg_begin(c, w, cap)) return 1;
+        for (auto& r : srcs) if (eg_copy(c, w, r.d, r.n, zero_to_min)) return 1;
+        k_eg_elastic_pts<<<blocks_for((long long)(nb - 1) * (extend_pts + 1), 128), 128, 0, c->stream>>>(
+            n->d_e_bins.as<double>(), nb, n->awr, n->kT, cutoff, extend_pts, w.out);
+        if (launch_check(c, "k_eg_elastic_pts")) return 1;
+        if (eg_sort_unique(c, w)) return 1;
+        k_eg_finish<<<1, 32, 0, c->stream>>>(w.uniq.as<double>(), w.n_unique.as<int>(), 0, 0, 0.0, w.res.as<int>(), w.status.as<int>());
+        if (launch_check(c, "k_eg_finish")) return 1;
+        if (eg_keep(c, w, n->d_ein_el, &n->n_ein_el, &st_acc)) return 1;
+    }
+    n->n_ein_inel = 0;
+    n->d_ein_inel.reset();
+    if (!only_el) {
+        EgWork w;
+        TmpBuf d_negQ;
+        if (eg_begin(c, w, (long long)n->n_ein_el + (long long)negQ.size() * std::max(nb - 2, 0) * (inel_extend_pts - 1) + 8)) return 1;
+        // Ein_inel = Ein_el(iEthresh:) (:208-210)
+        k_eg_finish<<<1, 32, 0, c->stream>>>(n->d_ein_el.as<double>(), nullptr, n->n_ein_el, 1, thresh, w.res.as<int>(), w.status.as<int>());
+        if (launch_check(c, "k_eg_finish")) return 1;
+        int res[2] = {0, 0}, st = 0;
+        CK(c, cudaMemcpyAsync(res, w.res.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(&st, w.status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (st & EG_ST_RANGE) return fail(c, "Value outside of array during binary search");
+        if (eg_copy(c, w, n->d_ein_el.as<double>() + res[1], n->n_ein_el - res[1], 0)) return 1;
+        if (!negQ.empty() && nb > 2 && inel_extend_pts > 1) {
+            if (tmp_upload(c, d_negQ, negQ.data(), negQ.size())) return 1;
+            const long long tot = (long long)negQ.size() * (nb - 2) * (inel_extend_pts - 1);
+            k_eg_inelastic_pts<<<blocks_for(tot, 256), 256, 0, c->stream>>>(d_negQ.as<double>(), (int)negQ.size(),
+                                                                          n->d_e_bins.as<double>(), nb, n->awr, thresh,
+                                                                          inel_extend_pts, w.out);
+            if (launch_check(c, "k_eg_inelastic_pts")) return 1;
+        }
+        if (eg_sort_unique(c, w)) return 1;
+        k_eg_finish<<<1, 32, 0, c->stream>>>(w.uniq.as<double>(), w.n_unique.as<int>(), 0, 2, top, w.res.as<int>(), w.status.as<int>());
+        if (launch_check(c, "k_eg_finish")) return 1;
+        if (eg_keep(c, w, n->d_ein_inel, &n->n_ein_inel, &st_acc)) return 1;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));   // negQ and the work buffers go out of scope
+    if (n_el) *n_el = n->n_ein_el;
+    if (n_inel) *n_inel = n->n_ein_inel;
+    if (status) *status = st_acc;
+    return 0;
+}
+
+int sab_egrid(Sab* s, const double* e_bins, int nb, int sab_epts_per_bin, int extend_pts, int* n_out, int* status)
+{
+    Ctx* c = s->ctx;
+    const SabDev& d = s->dev;
+    if (nb < 2 || d.n_in < 1) return fail(c, "ndppgpu_sab_egrid: empty group structure or table");
+    if (extend_pts < 0) return fail(c, "ndppgpu_sab_egrid: EXTEND_PTS must not be negative");
+    Timed tm(c, &c->pending_all);
+    TmpBuf d_bins;
+    if (tmp_upload(c, d_bins, e_bins, (size_t)nb)) return 1;
+    const bool has_el = d.el_e_in != nullptr && d.n_el_in > 0;
+    const double max_ein = has_el ? std::max(s->e_in_last, s->el_in_last) : s->e_in_last;
+    const bool all_zero = s->e_in_first == 0.0 && e_bins[0] == 0.0 && (!has_el || s->el_in_first == 0.0);
+    int st_acc = 0;
+    for (long long cap_cross = 1 << 18;; cap_cross *= 8) {
+        EgWork w;
+        if (eg_begin(c, w, (long long)d.n_in + d.n_el_in + nb + cap_cross)) return 1;
+        if (eg_copy(c, w, d.e_in, d.n_in, !all_zero) || (has_el && eg_copy(c, w, d.el_e_in, d.n_el_in, !all_zero)) ||
+            eg_copy(c, w, d_bins.as<double>(), nb, !all_zero))
+            return 1;
+        if (d.secondary_mode != SAB_SECONDARY_CONT && d.n_in > 1 && d.n_eout > 0) {
+            k_eg_sab_cross<<<blocks_for((long long)(d.n_in - 1) * d.n_eout, 128), 128, 0, c->stream>>>(d, d_bins.as<double>(), nb, w.out);
+            if (launch_check(c, "k_eg_sab_cross")) return 1;
+        }
+        unsigned long long cnt = 0;
+        CK(c, cudaMemcpyAsync(&cnt, w.count.p, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (cnt > (unsigned long long)w.cap) {
+            if (cap_cross > (1LL << 30)) return fail(c, "ndppgpu_sab_egrid: too many crossing points");
+            continue;
+        }
+        if (eg_sort_unique(c, w)) return 1;
+        k_eg_sab_cut<<<1, 32, 0, c->stream>>>(w.uniq.as<double>(), w.n_unique.as<int>(), max_ein, w.res.as<int>(), w.status.as<int>());
+        if (launch_check(c, "k_eg_sab_cut")) return 1;
+        int res[2] = {0, 0}, st = 0;
+        CK(c, cudaMemcpyAsync(res, w.res.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(&st, w.status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        st_acc |= st;
+        if (st & EG_ST_RANGE) return fail(c, "Value outside of array during binary search");
+        const int i_max = res[0];
+        if (sab_epts_per_bin == 0) {
+            s->n_ein = i_max;
+            if (dev_alloc(c, s->d_ein, (size_t)i_max * sizeof(double))) return 1;
+            CK(c, cudaMemcpyAsync(s->d_ein.p, w.uniq.p, (size_t)i_max * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            s->n_ein = (i_max - 1) * extend_pts + i_max;
+            if (dev_alloc(c, s->d_ein, (size_t)s->n_ein * sizeof(double))) return 1;
+            k_eg_sab_expand<<<blocks_for(i_max, 128), 128, 0, c->stream>>>(w.uniq.as<double>(), i_max, extend_pts, s->d_ein.as<double>());
+            if (launch_check(c, "k_eg_sab_expand")) return 1;
+        }
+        CK(c, cudaStreamSynchronize(c->stream));
+        break;
+    }
+    if (n_out) *n_out = s->n_ein;
+    if (status) *status = st_acc;
     return 0;
 }
 
@@ -1568,6 +1792,59 @@ int ndppgpu_inelastic_thinned(void* nuc, double* Ein, int NE, double print_tol, 
                          max_abs_err);
 }
 
+// create_Ein_grid (src/scatt.F90:166-236) on the device; the grids stay there (ndppgpu_nuclide_ein_grid)
+int ndppgpu_nuclide_create_ein_grid(void* nuc, int extend_pts, int inel_extend_pts, int* n_el, int* n_inel, int* status)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n) return fail(nullptr, "ndppgpu_nuclide_create_ein_grid: null argument");
+    CK(n->ctx, cudaSetDevice(n->ctx->device));
+    return create_ein_grid(n, extend_pts, inel_extend_pts, n_el, n_inel, status);
+}
+
+int ndppgpu_nuclide_ein_grid(void* nuc, int which, double* Ein, const double** d_Ein)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n) return fail(nullptr, "ndppgpu_nuclide_ein_grid: null argument");
+    Ctx* c = n->ctx;
+    if (which != 0 && which != 1) return fail(c, "ndppgpu_nuclide_ein_grid: which must be 0 (elastic) or 1 (inelastic)");
+    const DevBuf& b = which ? n->d_ein_inel : n->d_ein_el;
+    const int cnt = which ? n->n_ein_inel : n->n_ein_el;
+    if (n->n_ein_el == 0) return fail(c, "ndppgpu_nuclide_ein_grid: ndppgpu_nuclide_create_ein_grid has not been called");
+    if (d_Ein) *d_Ein = b.as<double>();
+    if (Ein && cnt > 0) {
+        CK(c, cudaSetDevice(c->device));
+        CK(c, cudaMemcpyAsync(Ein, b.p, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += (double)cnt * sizeof(double);
+    }
+    return 0;
+}
+
+// sab_egrid (src/sab.F90:460-568) on the device
+int ndppgpu_sab_egrid(void* sab, const double* e_bins, int n_bins, int sab_epts_per_bin, int extend_pts, int* n, int* status)
+{
+    Sab* s = (Sab*)sab;
+    if (!s || !e_bins) return fail(s ? s->ctx : nullptr, "ndppgpu_sab_egrid: null argument");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    return sab_egrid(s, e_bins, n_bins, sab_epts_per_bin, extend_pts, n, status);
+}
+
+int ndppgpu_sab_ein_grid(void* sab, double* Ein, const double** d_Ein)
+{
+    Sab* s = (Sab*)sab;
+    if (!s) return fail(nullptr, "ndppgpu_sab_ein_grid: null argument");
+    Ctx* c = s->ctx;
+    if (s->n_ein == 0) return fail(c, "ndppgpu_sab_ein_grid: ndppgpu_sab_egrid has not been called");
+    if (d_Ein) *d_Ein = s->d_ein.as<double>();
+    if (Ein) {
+        CK(c, cudaSetDevice(c->device));
+        CK(c, cudaMemcpyAsync(Ein, s->d_ein.p, (size_t)s->n_ein * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += (double)s->n_ein * sizeof(double);
+    }
+    return 0;
+}
+
 int ndppgpu_nuclide_free(void* nuc)
 {
     Nuclide* n = (Nuclide*)nuc;
@@ -1599,6 +1876,8 @@ int ndppgpu_sab_create(void* ctx, double awr, double kT, double threshold_inelas
     if (upload(c, s->e_in, inelastic_e_in, (size_t)n_inelastic_e_in) || upload(c, s->sigma, inelastic_sigma, (size_t)n_inelastic_e_in))
         return 1;
     d.e_in = s->e_in.as<double>(); d.sigma = s->sigma.as<double>();
+    if (n_inelastic_e_in > 0) { s->e_in_first = inelastic_e_in[0]; s->e_in_last = inelastic_e_in[n_inelastic_e_in - 1]; }
+    if (elastic_e_in && n_elastic_e_in > 0) { s->el_in_first = elastic_e_in[0]; s->el_in_last = elastic_e_in[n_elastic_e_in - 1]; }
     if (secondary_mode == SAB_SECONDARY_CONT) {
         if (!cont_n_e_out || !cont_e_out || !cont_pdf || !cont_mu) return fail(c, "ndppgpu_sab_create: continuous data missing");
         std::vector<long long> off(n_inelastic_e_in + 1, 0);
@@ -1769,8 +2048,8 @@ int ndppgpu_eval_libm(void* ctx, int fn, const double* x, long long n, double* y
 {
     Ctx* c = (Ctx*)ctx;
     if (!c || !x || !y) return fail(c, "ndppgpu_eval_libm: null argument");
-    if (fn < 0 || (fn > 3 && fn < 10) || fn > 12)
-        return fail(c, "ndppgpu_eval_libm: fn must be 0 (exp), 1 (expm1), 2 (sinh), 3 (cosh) or 10 .. 12 (free-gas primitives)");
+    if (fn < 0 || (fn > 4 && fn < 10) || fn > 12)
+        return fail(c, "ndppgpu_eval_libm: fn must be 0 (exp), 1 (expm1), 2 (sinh), 3 (cosh), 4 (log) or 10 .. 12 (free-gas primitives)");
     if (fn == 12 && (n & 1)) return fail(c, "ndppgpu_eval_libm: fn 12 divides x[i] by x[i ^ 1]: n must be even");
     if (n <= 0) return 0;
     CK(c, cudaSetDevice(c->device));

@@ -13,6 +13,8 @@ union, which equals the reference's two-pointer merge whenever neither input hol
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from .ace import ELASTIC, SAB_SECONDARY_CONT, Nuclide, SAlphaBeta, iter_slots
@@ -20,6 +22,16 @@ from .ace import ELASTIC, SAB_SECONDARY_CONT, Nuclide, SAlphaBeta, iter_slots
 MIN_EIN = 1e-14          # src/constants.F90:109
 EXTEND_PTS = 50          # src/constants.F90:81
 INEL_EXTEND_PTS = 30     # src/constants.F90:83
+
+
+def _exp(x) -> np.ndarray:
+    """exp / log of the C library, as the gfortran build calls them (numpy's SIMD loops differ from glibc in the last
+    bit for a few per cent of the arguments, which would move grid points)."""
+    return np.array([math.exp(v) for v in np.atleast_1d(x)])
+
+
+def _log(x: float) -> float:
+    return math.log(x) if x > 0.0 else float(np.log(x))
 
 
 def merge(a, b) -> np.ndarray:
@@ -86,7 +98,8 @@ def slot_summary(nuc: Nuclide, e_bins):
 
 
 def add_one_more_point(Ein):
-    return np.concatenate([Ein, [Ein[-1] * (1.0 + np.float32(1.0e-3))]])  # single-precision literal, :438
+    # the literal 1.0E-3 is single precision, promoted to double before the sum (:438)
+    return np.concatenate([Ein, [Ein[-1] * (1.0 + float(np.float32(1.0e-3)))]])
 
 
 def add_elastic_Eins(awr, kT, cutoff, E_bins, Ein, extend_pts=EXTEND_PTS):
@@ -97,21 +110,21 @@ def add_elastic_Eins(awr, kT, cutoff, E_bins, Ein, extend_pts=EXTEND_PTS):
         for g in range(len(E_bins) - 1):
             Ehi, Elo = E_bins[g + 1], E_bins[g]
             if Ehi <= cutoff:
-                dElo = (np.log(Ehi / (Ehi - lo_shift)) if Ehi - lo_shift > Elo else np.log(Ehi / 1e-11)) / extend_pts
-                pts = Ehi * np.exp(np.arange(-extend_pts, 0) * dElo)
+                dElo = (_log(Ehi / (Ehi - lo_shift)) if Ehi - lo_shift > Elo else _log(Ehi / 1e-11)) / extend_pts
+                pts = Ehi * _exp(np.arange(-extend_pts, 0) * dElo)
                 new.append(pts[pts >= Elo])
             elif Elo < cutoff:
-                dElo = np.log(cutoff / (cutoff - lo_shift)) / extend_pts
-                pts = cutoff * np.exp(np.arange(-extend_pts, 0) * dElo)
+                dElo = _log(cutoff / (cutoff - lo_shift)) / extend_pts
+                pts = cutoff * _exp(np.arange(-extend_pts, 0) * dElo)
                 new.append(pts[pts > Elo])
         if new:
             Ein = merge(np.sort(np.concatenate(new)), Ein)
-    dEhi = 7.0 * np.log(1.0 / alpha) / extend_pts if alpha > 0 else np.inf
+    dEhi = 7.0 * _log(1.0 / alpha) / extend_pts if alpha > 0 else np.inf
     new = []
     for g in range(len(E_bins) - 1):
         if E_bins[g] == 0.0:
             continue
-        pts = E_bins[g] * np.exp(np.arange(1, extend_pts) * dEhi)
+        pts = E_bins[g] * _exp(np.arange(1, extend_pts) * dEhi)
         keep = pts < E_bins[g + 1]
         n = int(np.argmin(keep)) if not keep.all() else len(pts)  # the reference exits at the first failure
         new.append(pts[:n])
@@ -144,8 +157,8 @@ def add_inelastic_Eins(slots, awr, E_bins, thresh, Ein, inel_extend_pts=INEL_EXT
             Elo = max(Elo, thresh) if not np.isnan(Elo) else thresh
             Ehi = max(Ehi, thresh) if not np.isnan(Ehi) else thresh
             if Elo != Ehi:
-                dE = np.log(Ehi / Elo) / inel_extend_pts
-                new.append(Elo * np.exp(np.arange(1, inel_extend_pts) * dE))
+                dE = _log(Ehi / Elo) / inel_extend_pts
+                new.append(Elo * _exp(np.arange(1, inel_extend_pts) * dE))
         if new:
             Ein = merge(np.sort(np.concatenate(new)), Ein)
     return Ein
@@ -215,10 +228,10 @@ def sab_egrid(sab: SAlphaBeta, energy_bins, sab_epts_per_bin=10, extend_pts=EXTE
         return base.copy()
     out = []
     for k in range(i_max - 1):
-        dE = np.log(base[k + 1] / base[k]) / float(extend_pts + 1)
+        dE = _log(base[k + 1] / base[k]) / float(extend_pts + 1)
         seg = np.empty(extend_pts + 1)
         seg[0] = base[k]
-        step = np.exp(dE)
+        step = math.exp(dE)
         for q in range(1, extend_pts + 1):   # Ein(j) = Ein(j-1) * exp(dE), sequentially (:560-563)
             seg[q] = seg[q - 1] * step
         out.append(seg)

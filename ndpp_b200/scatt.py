@@ -134,6 +134,23 @@ class DeviceNuclide:
         check(self.lib.ndppgpu_inelastic_dev(self.h, d_Ein.data_ptr(), int(d_Ein.numel()), d_out.data_ptr(),
                                              d_nu.data_ptr() if d_nu is not None else None), self.ctx.h)
 
+    def create_ein_grid(self, extend_pts=50, inel_extend_pts=30, host=True):
+        """create_Ein_grid (src/scatt.F90:166-236) on the device.  Returns (Ein_el, Ein_inel or None, status) as host
+        arrays, or -- host=False -- ((device pointer, n_el), (device pointer, n_inel) or None, status) for the *_dev calls."""
+        n_el, n_inel, st = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self.lib.ndppgpu_nuclide_create_ein_grid(self.h, extend_pts, inel_extend_pts, C.byref(n_el), C.byref(n_inel),
+                                                       C.byref(st)), self.ctx.h)
+        out = []
+        for which, n in ((0, n_el.value), (1, n_inel.value)):
+            if n == 0:
+                out.append(None)
+                continue
+            ptr = C.c_void_p()
+            arr = np.empty(n) if host else None
+            check(self.lib.ndppgpu_nuclide_ein_grid(self.h, which, dp(arr), C.byref(ptr)), self.ctx.h)
+            out.append(arr if host else (ptr.value, n))
+        return out[0], out[1], st.value
+
     def clear(self):
         """rxn_data(i) % clear() (src/scatt.F90:153-155)."""
         if self.h:
@@ -203,6 +220,16 @@ class DeviceSab:
         check(self.lib.ndppgpu_sab(self.h, dp(eb), len(eb), scatt_type, order, dp(Ein), len(Ein), dp(out), dp(el),
                                    dp(inel)), self.ctx.h)
         return (out, el, inel) if parts else out
+
+    def egrid(self, energy_bins, sab_epts_per_bin=10, extend_pts=50):
+        """sab_egrid (src/sab.F90:460-568) on the device: (Ein, status)."""
+        eb = f64(energy_bins)
+        n, st = C.c_int(0), C.c_int(0)
+        check(self.lib.ndppgpu_sab_egrid(self.h, dp(eb), len(eb), sab_epts_per_bin, extend_pts, C.byref(n), C.byref(st)),
+              self.ctx.h)
+        out = np.empty(n.value)
+        check(self.lib.ndppgpu_sab_ein_grid(self.h, dp(out), None), self.ctx.h)
+        return out, st.value
 
     def calc_dev(self, energy_bins, scatt_type, order, d_Ein, d_out):
         eb = f64(energy_bins)

@@ -613,6 +613,41 @@ int ref_nuclide_inelastic(void *h, const double *Ein, int NE, double *inel_mat, 
     return ref_error_count();
 }
 
+/* calc_scatt's preamble of create_Ein_grid (src/scatt.F90:89-140): inel_thresh = the lowest threshold energy of the
+ * initialised non-elastic slots (from energy_bins(size)), cutoff = the elastic slot's freegas_cutoff; then egrid_ref.c */
+int ref_create_ein_grid(int n_slots, const int *is_init, const int *MT, const double *Q_value, const double *const *E_grid,
+                        const int *NE, const double *E_bins, int nb, const double *nuc_grid, int n_grid, double awr,
+                        double kT, double cutoff, double thresh, int extend_pts, int inel_extend_pts, double *Ein_el,
+                        int *n_el, double *Ein_inel, int *n_inel, int cap);
+int ref_nuclide_create_ein_grid(void *h, int extend_pts, int inel_extend_pts, double *Ein_el, int *n_el, double *Ein_inel,
+                                int *n_inel, int cap)
+{
+    ref_nuclide *nuc = (ref_nuclide *)h;
+    int ns = nuc->n_slots, i, rc;
+    int *is_init = (int *)calloc((size_t)ns + 1, sizeof(int)), *MT = (int *)calloc((size_t)ns + 1, sizeof(int));
+    int *NE = (int *)calloc((size_t)ns + 1, sizeof(int));
+    double *Q = (double *)calloc((size_t)ns + 1, sizeof(double));
+    const double **eg = (const double **)calloc((size_t)ns + 1, sizeof(double *));
+    double inel_thresh = A1(nuc->e_bins, nuc->n_bins), cutoff = ZERO;
+    for (i = 0; i < ns; ++i) {
+        ref_slot *s = &nuc->slots[i];
+        is_init[i] = s->is_init;
+        if (!s->is_init) continue;
+        MT[i] = s->rxn->MT;
+        Q[i] = s->rxn->Q;
+        NE[i] = s->NE;
+        eg[i] = s->E_grid;
+        if (s->rxn->MT == REF_ELASTIC)
+            cutoff = s->freegas_cutoff;
+        else if (A1(nuc->energy, s->rxn->threshold) < inel_thresh)
+            inel_thresh = A1(nuc->energy, s->rxn->threshold);
+    }
+    rc = ref_create_ein_grid(ns, is_init, MT, Q, eg, NE, nuc->e_bins, nuc->n_bins, nuc->energy, nuc->n_grid, nuc->awr, nuc->kT,
+                             cutoff, inel_thresh, extend_pts, inel_extend_pts, Ein_el, n_el, Ein_inel, n_inel, cap);
+    free(is_init); free(MT); free(NE); free(Q); free(eg);
+    return rc;
+}
+
 void ref_nuclide_free(void *h)
 {
     ref_nuclide *nuc = (ref_nuclide *)h;

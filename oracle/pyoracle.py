@@ -63,6 +63,9 @@ def lib() -> C.CDLL:
         L.ref_nuclide_slot_info.argtypes = [C.c_void_p, C.c_int, c_ip]
         L.ref_nuclide_slot_row_np.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_nuclide_slot_egrid.argtypes = [C.c_void_p, C.c_int, c_dp]
+        L.ref_nuclide_create_ein_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_int]
+        L.ref_sab_egrid.argtypes = [c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_int,
+                                    c_dp, C.c_int]
         L.ref_nuclide_get_table.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_ip]
         L.ref_nuclide_set_table.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp]
         L.ref_nuclide_interp_distro.argtypes = [C.c_void_p, C.c_int, C.c_double, c_dp]
@@ -265,6 +268,18 @@ class RefNuclide:
         self.L.ref_nuclide_get_table(self.h, s, iE, dp(d), dp(Eo), dp(pdf), dp(cdf), C.byref(INTT))
         return d.reshape(NP, M).T.copy(), Eo, pdf, cdf, INTT.value
 
+    def create_ein_grid(self, extend_pts=50, inel_extend_pts=30):
+        """create_Ein_grid (src/scatt.F90:166-236) with calc_scatt's inel_thresh / cutoff: (Ein_el, Ein_inel or None)."""
+        cap = 1 << 16
+        while True:
+            el, inel = np.zeros(cap), np.zeros(cap)
+            n_el, n_inel = C.c_int(0), C.c_int(0)
+            rc = self.L.ref_nuclide_create_ein_grid(self.h, extend_pts, inel_extend_pts, dp(el), C.byref(n_el), dp(inel),
+                                                    C.byref(n_inel), cap)
+            if rc == 0:
+                return el[:n_el.value].copy(), (inel[:n_inel.value].copy() if n_inel.value else None)
+            cap = 2 * max(n_el.value, n_inel.value)
+
     def slot_egrid(self, s):
         ne = self.slot_info(s)["NE"]
         out = np.zeros(ne)
@@ -303,6 +318,27 @@ class RefNuclide:
             self.close()
         except Exception:
             pass
+
+
+def sab_egrid(sab, e_bins, sab_epts_per_bin=10, extend_pts=50):
+    """sab_egrid (src/sab.F90:460-568)."""
+    L = lib()
+    e_bins = f64(e_bins)
+    ein = f64(sab.inelastic_e_in)
+    if int(sab.secondary_mode) == 2:                   # continuous secondary energies: no crossing points (:497)
+        n_eo, eo = 0, None
+    else:
+        n_eo = np.asarray(sab.inelastic_e_out).reshape(len(ein), -1).shape[1]
+        eo = f64(sab.inelastic_e_out)                  # [n_e_in][n_e_out], C order = the Fortran (j, i) layout
+    eel = f64(sab.elastic_e_in) if sab.elastic_e_in is not None else None
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap)
+        n = L.ref_sab_egrid(dp(ein), len(ein), dp(eel), 0 if eel is None else len(eel), dp(eo), n_eo,
+                            int(sab.secondary_mode), dp(e_bins), len(e_bins), sab_epts_per_bin, extend_pts, dp(out), cap)
+        if n >= 0:
+            return out[:n].copy()
+        cap = -n
 
 
 def sab_calc(sab, e_bins, order, Ein, parts=False, tabular=False):

@@ -17,7 +17,7 @@ static inline uint64_t splitmix(uint64_t& s)
 
 static inline uint64_t bits(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 
-// fn: 0 exp, 1 expm1, 2 sinh, 3 cosh.  Arguments: uniform in [lo, hi] (mode 0) or sign * 10^uniform(lo, hi) (mode 1).
+// fn: 0 exp, 1 expm1, 2 sinh, 3 cosh, 4 log.  Arguments: uniform in [lo, hi] (mode 0) or sign * 10^uniform(lo, hi) (mode 1).
 // Returns the number of arguments whose results differ from libm's in any bit; *first_bad = one such argument.
 extern "C" long long libm_exact_mismatches(int fn, double lo, double hi, long long n, unsigned long long seed, int mode,
                                            double* first_bad)
@@ -41,6 +41,7 @@ extern "C" long long libm_exact_mismatches(int fn, double lo, double hi, long lo
             case 0: a = ndpp::lm::exp_(x); b = exp(x); break;
             case 1: a = ndpp::lm::expm1_(x); b = expm1(x); break;
             case 2: a = ndpp::lm::sinh_(x); b = sinh(x); break;
+            case 4: a = ndpp::lm::log_(x); b = log(x); break;
             default: a = ndpp::lm::cosh_(x); b = cosh(x); break;
             }
             if (bits(a) != bits(b) && !(a != a && b != b)) {
@@ -58,11 +59,11 @@ extern "C" long long libm_exact_mismatches(int fn, double lo, double hi, long lo
 extern "C" void libm_host_eval(int fn, const double* x, double* y, long long n)
 {
 #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < n; ++i) y[i] = fn == 2 ? sinh(x[i]) : fn == 3 ? cosh(x[i]) : fn == 1 ? expm1(x[i]) : exp(x[i]);
+    for (long long i = 0; i < n; ++i) y[i] = fn == 4 ? log(x[i]) : fn == 2 ? sinh(x[i]) : fn == 3 ? cosh(x[i]) : fn == 1 ? expm1(x[i]) : exp(x[i]);
 }
 extern "C" void libm_port_eval(int fn, const double* x, double* y, long long n)
 {
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < n; ++i)
-        y[i] = fn == 2 ? ndpp::lm::sinh_(x[i]) : fn == 3 ? ndpp::lm::cosh_(x[i]) : fn == 1 ? ndpp::lm::expm1_(x[i]) : ndpp::lm::exp_(x[i]);
+        y[i] = fn == 4 ? ndpp::lm::log_(x[i]) : fn == 2 ? ndpp::lm::sinh_(x[i]) : fn == 3 ? ndpp::lm::cosh_(x[i]) : fn == 1 ? ndpp::lm::expm1_(x[i]) : ndpp::lm::exp_(x[i]);
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ndppgpu.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert lib.ndppgpu_abi_version() == 2
+    assert lib.ndppgpu_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -16,13 +16,14 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "native", "libm_exact_check.cpp")
 SO = os.path.join(HERE, "native", "libm_exact_check.so")
-FN = {"exp": 0, "expm1": 1, "sinh": 2, "cosh": 3}
+FN = {"exp": 0, "expm1": 1, "sinh": 2, "cosh": 3, "log": 4}
 
 
 @pytest.fixture(scope="module")
 def chk():
     deps = [SRC, os.path.join(HERE, "..", "ndpp_b200", "csrc", "libm_exact.cuh"),
-            os.path.join(HERE, "..", "ndpp_b200", "csrc", "exp_table.inc")]
+            os.path.join(HERE, "..", "ndpp_b200", "csrc", "exp_table.inc"),
+            os.path.join(HERE, "..", "ndpp_b200", "csrc", "log_table.inc")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", SO, SRC])
     L = C.CDLL(SO)
@@ -56,6 +57,58 @@ def test_host_build_reproduces_the_running_libm(chk, name):
         bad = chk.libm_exact_mismatches(FN[name], lo, hi, n, 20261018 + 16 * FN[name] + k, mode, C.byref(bad_x))
         assert bad == 0, f"{name} on [{lo}, {hi}] mode {mode}: {bad} of {n} results differ from libm, e.g. at x = {bad_x.value!r}"
         total += n
+    assert total >= 100_000_000
+
+
+# log: the ratios the grid builders pass (Ehi / Elo of neighbouring points and of group edges: 1 .. 1e12), the window
+# around 1 with its own polynomial, every binade, subnormal arguments
+LOG_RANGES = [(0.9, 1.1, 0), (0.93, 1.07, 0), (0.0, 4.0, 0), (1.0, 1.0e6, 0), (0.0, 12.0, 1), (-320.0, 308.0, 1)]
+
+
+@pytest.mark.skipif(not _has_fma(), reason="the restated libm copies are the ones glibc selects on FMA + AVX2 CPUs")
+def test_host_build_of_log_reproduces_the_running_libm(chk):
+    total = 0
+    for k, (lo, hi, mode) in enumerate(LOG_RANGES):
+        n = 24_000_000
+        bad_x = C.c_double(0.0)
+        bad = chk.libm_exact_mismatches(FN["log"], lo, hi, n, 20261019 + k, mode, C.byref(bad_x))
+        assert bad == 0, f"log on [{lo}, {hi}] mode {mode}: {bad} of {n} results differ from libm, e.g. at x = {bad_x.value!r}"
+        total += n
+    assert total >= 100_000_000
+
+
+def test_special_arguments_of_log(chk):
+    x = np.array([0.0, -0.0, 5e-324, 1e-320, 2.2250738585072014e-308, 1.0, np.nextafter(1.0, 0), np.nextafter(1.0, 2),
+                  1.0 - 2.0 ** -4, np.nextafter(1.0 - 2.0 ** -4, 0), 1.0 + 265.0 / 4096.0, np.nextafter(1.0 + 265.0 / 4096.0, 0), 2.0,
+                  1e308, 1.7976931348623157e308, np.inf, -1.0, -np.inf, np.nan])
+    a, b = np.empty_like(x), np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    with np.errstate(all="ignore"):
+        chk.libm_port_eval(FN["log"], x.ctypes.data_as(dp), a.ctypes.data_as(dp), len(x))
+        chk.libm_host_eval(FN["log"], x.ctypes.data_as(dp), b.ctypes.data_as(dp), len(x))
+    same = (a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), (x[~same], a[~same], b[~same])
+
+
+@pytest.mark.gpu
+def test_device_log_carries_the_host_libm_bits(chk):
+    from ndpp_b200 import scatt
+    ctx = scatt.default_context()
+    rng = np.random.default_rng(404)
+    dp = C.POINTER(C.c_double)
+    total = 0
+    for lo, hi, mode, reps in ((0.9, 1.1, 0, 2), (0.0, 4.0, 0, 2), (1.0, 1.0e6, 0, 2), (0.0, 12.0, 1, 2), (-320.0, 308.0, 1, 2)):
+        for _ in range(reps):
+            n = 10_000_000
+            x = rng.uniform(lo, hi, n)
+            if mode == 1:
+                x = 10.0 ** x
+            ref = np.empty_like(x)
+            chk.libm_host_eval(FN["log"], x.ctypes.data_as(dp), ref.ctypes.data_as(dp), n)
+            got = ctx.eval_libm(FN["log"], x)
+            bad = np.nonzero(got.view(np.uint64) != ref.view(np.uint64))[0]
+            assert bad.size == 0, f"log: {bad.size} of {n} device results differ from libm, e.g. x = {x[bad[0]]!r}"
+            total += n
     assert total >= 100_000_000
 
 
