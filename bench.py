@@ -428,6 +428,7 @@ def run_b200(args):
         if world == 1:
             dn.clear()
             extra["configs"] = run_configs(ctx, peak, sample_cpu=not args.no_cpu_baseline)
+            extra["ein_grid"] = run_ein_grid(ctx, nuc, e_bins, params, sample_cpu=not args.no_cpu_baseline)
             cgroup = Group(1, devices=[local])
             extra["c5_library"] = library.run_c5(cgroup, args.c5_nuclides)
             cgroup.close()
@@ -495,6 +496,34 @@ def _cpu_rate_nuclide(nuc, e_bins, params, Ein_el, Ein_inel, n, threads, counter
     cnt = pyoracle.freegas_counters(reset=True) if counters else None
     rn.close()
     return ev / dt, len(pick(Ein_el)), cnt
+
+
+def run_ein_grid(ctx, nuc, e_bins, params, sample_cpu=True):
+    """Row N3: create_Ein_grid (src/scatt.F90:166-536) of the workload's nuclide on the device (second pass; the grids
+    stay on the device, the timed call returns their lengths) beside the oracle's literal chain of merges on one host
+    core (the routine is serial in the reference), and whether the two grids agree in every bit."""
+    from ndpp_b200 import scatt
+    dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+    for _ in range(2):
+        ctx.stats(reset=True)
+        t0 = time.perf_counter()
+        (p_el, n_el), inel, status = dn.create_ein_grid(host=False)
+        wall = time.perf_counter() - t0
+    st = ctx.stats(reset=True)
+    row = {"routine": "create_Ein_grid (src/scatt.F90:166-536)", "n_el": n_el, "n_inel": inel[1] if inel else 0,
+           "device_ms": wall * 1e3, "kernel_ms": st["kernel_ms"], "launches": int(st["launches"]), "status": status}
+    if sample_cpu:
+        from oracle import pyoracle
+        el, inl, _ = dn.create_ein_grid()
+        rn = pyoracle.RefNuclide(nuc, e_bins, params)
+        t0 = time.perf_counter()
+        r_el, r_inl = rn.create_ein_grid()
+        row["cpu"] = {"ms": (time.perf_counter() - t0) * 1e3, "cores": 1, "kind": "port"}
+        rn.close()
+        row["bit_identical_to_oracle"] = bool(np.array_equal(el, r_el) and (inl is None) == (r_inl is None)
+                                              and (inl is None or np.array_equal(inl, r_inl)))
+    dn.clear()
+    return row
 
 
 def run_configs(ctx, peak_tflops, sample_cpu=True):

@@ -308,6 +308,19 @@ public:
         inel_mat.resize(kept * w);
         if (nuscatt) nuinel_mat.resize(kept * w);
     }
+    // create_Ein_grid(rxn_data, E_bins, nuc % energy, awr, kT, cutoff, thresh, Ein_el, Ein_inel) (src/scatt.F90:166-236)
+    // on the device; Ein_inel comes back empty for a nuclide with elastic scattering only (unallocated in the reference)
+    void create_Ein_grid(std::vector<double>& Ein_el, std::vector<double>& Ein_inel, int extend_pts = 50,
+                         int inel_extend_pts = 30, int* status = nullptr) const
+    {
+        if (group_) fatal_error("create_Ein_grid: call it on the nuclide of one device (the grids are inputs of the group calls)");
+        int n_el = 0, n_inel = 0;
+        ctx_.check(ndppgpu_nuclide_create_ein_grid(h_, extend_pts, inel_extend_pts, &n_el, &n_inel, status));
+        Ein_el.assign((size_t)n_el, 0.0);
+        Ein_inel.assign((size_t)n_inel, 0.0);
+        ctx_.check(ndppgpu_nuclide_ein_grid(h_, 0, Ein_el.data(), nullptr));
+        if (n_inel > 0) ctx_.check(ndppgpu_nuclide_ein_grid(h_, 1, Ein_inel.data(), nullptr));
+    }
     // rxn_data(i) % clear() (src/scatt.F90:153-155)
     void clear()
     {

@@ -27,6 +27,7 @@ module ndpp_gpu
   public :: ndppgpu_init, ndppgpu_finalize, ndppgpu_last_error
   public :: ndppgpu_nuclide_create, ndppgpu_nuclide_add_reaction, ndppgpu_convert_distro
   public :: ndppgpu_elastic, ndppgpu_inelastic, ndppgpu_nuclide_free
+  public :: ndppgpu_nuclide_create_ein_grid, ndppgpu_nuclide_ein_grid, ndppgpu_sab_egrid, ndppgpu_sab_ein_grid
   public :: ndppgpu_elastic_thinned, ndppgpu_inelastic_thinned
   public :: ndppgpu_apply_tol, ndppgpu_thin_grid
   public :: ndppgpu_sab_create, ndppgpu_sab, ndppgpu_sab_free
@@ -184,6 +185,25 @@ module ndpp_gpu
       integer(c_int)                :: rc
     end function ndppgpu_inelastic_thinned
 
+    ! create_Ein_grid (src/scatt.F90:166-236) on the device; lengths back, then ndppgpu_nuclide_ein_grid copies a grid
+    function ndppgpu_nuclide_create_ein_grid(nuc, extend_pts, inel_extend_pts, n_el, n_inel, status) &
+         bind(C, name="ndppgpu_nuclide_create_ein_grid") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value          :: nuc
+      integer(c_int), value       :: extend_pts, inel_extend_pts
+      integer(c_int), intent(out) :: n_el, n_inel, status
+      integer(c_int)              :: rc
+    end function ndppgpu_nuclide_create_ein_grid
+
+    ! which = 0: Ein_el, 1: Ein_inel; d_Ein: c_null_ptr, or the address of a type(c_ptr) that receives the device pointer
+    function ndppgpu_nuclide_ein_grid(nuc, which, Ein, d_Ein) bind(C, name="ndppgpu_nuclide_ein_grid") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value          :: nuc, d_Ein
+      integer(c_int), value       :: which
+      real(c_double), intent(out) :: Ein(*)
+      integer(c_int)              :: rc
+    end function ndppgpu_nuclide_ein_grid
+
     function ndppgpu_nuclide_free(nuc) bind(C, name="ndppgpu_nuclide_free") result(rc)
       import :: c_int, c_ptr
       type(c_ptr), value :: nuc
@@ -244,6 +264,24 @@ module ndpp_gpu
       real(c_double), intent(out) :: scatt_mat(*)
       integer(c_int)              :: rc
     end function ndppgpu_sab
+
+    ! sab_egrid (src/sab.F90:460-568) on the device
+    function ndppgpu_sab_egrid(sab, e_bins, n_bins, sab_epts_per_bin, extend_pts, n, status) &
+         bind(C, name="ndppgpu_sab_egrid") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value          :: sab
+      real(c_double), intent(in)  :: e_bins(*)
+      integer(c_int), value       :: n_bins, sab_epts_per_bin, extend_pts
+      integer(c_int), intent(out) :: n, status
+      integer(c_int)              :: rc
+    end function ndppgpu_sab_egrid
+
+    function ndppgpu_sab_ein_grid(sab, Ein, d_Ein) bind(C, name="ndppgpu_sab_ein_grid") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value          :: sab, d_Ein
+      real(c_double), intent(out) :: Ein(*)
+      integer(c_int)              :: rc
+    end function ndppgpu_sab_ein_grid
 
     function ndppgpu_sab_free(sab) bind(C, name="ndppgpu_sab_free") result(rc)
       import :: c_int, c_ptr

@@ -43,6 +43,7 @@ struct Ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
     int sm_count = 148;
     int fg_first_cap = 4096;  // NDPPGPU_FG_CAP: first-attempt frontier capacity of the free-gas scratch (tests)
+    int fg_chunk = 0;        // NDPPGPU_FG_CHUNK=128: the chunked instantiation of the free-gas kernel (default 0: whole levels)
     int fg_split_depth = 0;  // NDPPGPU_FG_SPLIT: levels of the outer recursion below its node that one work item walks (0..3).
                              // C3 293.6 K / 1200 K, kernel ms: 2 -> 317 / 231, 1 -> 275 / 218, 0 (one node per item) -> 258 / 205:
                              // the late generations hold few, heavy items and are bound by the longest chain of inner integrals
@@ -790,8 +791,9 @@ int elastic_dev(Nuclide* n, const double* d_Ein, int NE, double* d_out)
                 unsigned long long tails[2] = {0, 0};
                 {
                     CK(c, cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), c->stream));
-                    CK(c, cudaFuncSetAttribute(k_freegas_items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgShared)));
-                    k_freegas_items<<<max_blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
+                    auto kern = c->fg_chunk ? k_freegas_items<128> : k_freegas_items<0>;
+                    CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FgShared)));
+                    kern<<<max_blocks, FG_WARPS_PER_BLOCK * 32, sizeof(FgShared), c->stream>>>(
                         n->dev, s->dev, d_Ein, idx.as<int>(), rows, s->iso_rows ? 1 : 0, q,
                         d_counter.as<unsigned long long>(), (FgPair*)align_up(d_frames.p, 128), (double*)align_up(d_nvals.p, 128),
                         d_nchilds.as<int>(), (int)capF, (int)capN, d_ovf.as<int>());
@@ -1247,6 +1249,8 @@ int ndppgpu_init(int device, void** ctx)
         if (e && std::atoi(e) >= 2) c->fg_first_cap = std::atoi(e);
         e = std::getenv("NDPPGPU_FG_SPLIT");
         if (e && e[0] && std::atoi(e) >= 0) c->fg_split_depth = std::min(std::atoi(e), (int)FG_MAX_SPLIT_DEPTH);
+        e = std::getenv("NDPPGPU_FG_CHUNK");
+        if (e && std::atoi(e) > 0) c->fg_chunk = 128;
         e = std::getenv("NDPPGPU_FG_QUEUE");
         if (e && std::atoll(e) >= 2) c->fg_queue_cap = std::atoll(e);
     }

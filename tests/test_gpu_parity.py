@@ -458,6 +458,30 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     assert items[0] < items[1] < items[2] < items[3] and items[4] == items[1]
 
 
+def test_freegas_chunked_walk_does_not_change_the_bits(scatt, monkeypatch):
+    """The inner (mu) recursion is walked level by level, or 128 intervals of a level at a time with the forest below a
+    chunk folded before the next chunk starts (NDPPGPU_FG_CHUNK; csrc/kernels_freegas.cuh: fg_warp_simpson_mu): same intervals,
+    same value tree, so the same bits -- here on the three heaviest kinds of columns (E_in far below, near and above kT),
+    with a small first-attempt scratch so that the retry with the worst-case scratch runs through the chunked walk too."""
+    from ndpp_b200.capi import Context
+    nuc, e_bins, params, Ein = synth.c3_h1_freegas(n_ein=1000)
+    Ein = Ein[[0, 450, 900]]
+    outs = []
+    for chunk, cap in ((None, None), ("128", None), ("128", "64")):
+        for name, val in (("NDPPGPU_FG_CHUNK", chunk), ("NDPPGPU_FG_CAP", cap)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
+        ctx = Context(-1)
+        dn = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
+        outs.append(dn.elastic(Ein))
+        dn.clear()
+    assert np.any(outs[0] != 0)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+
+
 def test_unitbase_and_file6_cm_leg_heavy_target_limit(scatt, oracle):
     """The CUDA path against closed forms where the reference holds no test (unit-base interpolation +
     integrate_file6_cm_leg, A -> infinity, separable tables; tests/util.py: heavy_limit_law61), and against the oracle."""

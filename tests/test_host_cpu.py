@@ -67,7 +67,7 @@ def test_create_ein_grid_shapes():
     el, inel = egrid.create_Ein_grid(nuc, eb)
     assert np.all(np.diff(el) > 0) and np.all(np.diff(inel) > 0)
     assert el[0] == egrid.MIN_EIN                       # the 0.0 group edge becomes MIN_EIN (array_merge.F90:49-53)
-    assert el[-1] == np.float64(20.0) * (1.0 + np.float32(1e-3)) and inel[-1] == el[-1]
+    assert el[-1] == 20.0 * (1.0 + float(np.float32(1e-3))) and inel[-1] == el[-1]   # ONE + 1.0E-3 in double (:438)
     thr = min(nuc.energy[r.threshold - 1] for r in nuc.reactions if r.MT != 2)
     assert inel[0] <= thr < inel[1] or inel[0] == thr
     assert len(inel) > len(el)                          # (INEL_EXTEND_PTS-1) points per level and group edge
