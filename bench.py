@@ -530,7 +530,7 @@ def run_configs(ctx, peak_tflops, sample_cpu=True):
     """evals/s, kernel time, roofline fraction (algorithmic flops of SURVEY 8d / CUDA-event kernel time / measured FP64
     peak; HBM GB/s for the memory-bound stage 2 of the continuous S(a,b) path) and the sampled CPU rate of every
     BASELINE configuration that is not the headline one.  Second pass of each (the first loads kernels and grows the pool)."""
-    from ndpp_b200 import ace, egrid, scatt, synth
+    from ndpp_b200 import ace, scatt, synth
     threads = os.cpu_count() or 1
     rows = []
     try:
@@ -597,10 +597,10 @@ def run_configs(ctx, peak_tflops, sample_cpu=True):
     for name, sab, tab in (("C4 H-in-H2O S(a,b) discrete (skewed), P5", synth.c4_sab("skewed"), False),
                            ("C4 H-in-H2O S(a,b) continuous, P5", synth.c4_sab("cont", n_eout=400), False),
                            ("C4 H-in-H2O S(a,b) discrete (skewed), 16-bin cosine histogram", synth.c4_sab("skewed"), True)):
-        Ein = egrid.sab_egrid(sab, e_bins)
         order = 16 if tab else 5
         L = order if tab else order + 1
         ds = scatt.DeviceSab(sab, ctx)
+        Ein, _ = ds.egrid(e_bins)            # sab_egrid (src/sab.F90:460-568) on the device
         for _ in range(2):
             ctx.stats(reset=True)
             t0 = time.perf_counter()

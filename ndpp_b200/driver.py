@@ -11,7 +11,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import chi, egrid, output
+from . import chi, output
 from .ace import SCATT_TYPE_LEGENDRE, Nuclide, Params
 from .capi import Context, check, dp, f64
 from .scatt import DeviceNuclide
@@ -55,13 +55,14 @@ def preprocess_nuclide(nuc: Nuclide, energy_bins, params: Params, print_tol: flo
                        library_file: Optional[str] = None, lib_format: str = output.BINARY,
                        integrate_chi: bool = False) -> NuclideResult:
     """One nuclide through src/ndpp.F90:560-702.  `thin_tol` is the fraction the reference derives from the
-    user's percentage (`0.01 * thinning_tol`, :337); E_in grids default to create_Ein_grid (src/scatt.F90:166)."""
+    user's percentage (`0.01 * thinning_tol`, :337); E_in grids default to create_Ein_grid (src/scatt.F90:166), built on
+    the device after convert_distro as in calc_scatt (:107-139)."""
     if params.scatt_type != SCATT_TYPE_LEGENDRE:
         raise ValueError("tabular scattering of ACE nuclides is NOT YET IMPLEMENTED in the reference")
-    if Ein_el is None:
-        Ein_el, Ein_inel = egrid.create_Ein_grid(nuc, energy_bins)
     dn = DeviceNuclide(nuc, energy_bins, params, ctx)
     try:
+        if Ein_el is None:
+            Ein_el, Ein_inel, _ = dn.create_ein_grid()
         xe, el, _, ce, ee = _thinned(dn, False, Ein_el, print_tol, thin_tol, energy_bins, False)
         xi = inel = nu = None
         ci = ei = 0.0
