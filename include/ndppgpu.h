@@ -134,8 +134,9 @@ int ndppgpu_interp_distro(void *nuc, int slot, const double *Ein, int NE, double
  * (src/constants.F90:85-86: 50 / 30).  The grids stay on the device; *n_el / *n_inel receive their lengths (*n_inel = 0
  * for a nuclide with elastic scattering only: Ein_inel stays unallocated in the reference).  The points the reference
  * places with log / exp carry the bits of the host's C library (csrc/libm_exact.cuh).  *status (nullable): bit 1 a
- * critical energy of add_inelastic_Eins was NaN and its points were left out (the reference's merge would be
- * poisoned), bit 2 an input array held a repeated value (dropped here; the reference's merge keeps some). */
+ * critical energy of add_inelastic_Eins was NaN and its points were left out (as the reference's merge ends up doing:
+ * it drops an all-NaN array), bit 2 an input array held a repeated value (dropped here; the reference's merge keeps
+ * some of them). */
 int ndppgpu_nuclide_create_ein_grid(void *nuc, int extend_pts, int inel_extend_pts, int *n_el, int *n_inel, int *status);
 /* which = 0: Ein_el, 1: Ein_inel.  Ein (nullable): host array of the length returned above; d_Ein (nullable) receives
  * the device pointer (valid until the next create_ein_grid / nuclide_free) for ndppgpu_elastic_dev / _inelastic_dev. */

@@ -16,12 +16,14 @@
 // the cuts (iEthresh, E_bins(size)) and add_one_more_point.  The grids stay on the device for ndppgpu_group_set_grids /
 // the *_dev entry points; nothing returns to the host but their lengths.
 //
-// Where this differs from the chain of merges (flagged in the status word, never silently):
+// Where this differs from the chain of merges, or meets one of its quirks (reported in the status word):
 //   * a zero that meets a larger value becomes MIN_EIN in merge; every zero candidate is replaced before the sort when
 //     some merged array does not start with zero (the chain would keep a second MIN_EIN if two arrays held a zero);
 //   * values repeated inside one input array survive a merge in some positions; here every repeat is dropped (bit 2);
-//   * a critical energy that is NaN (negative discriminant in add_inelastic_Eins) poisons the reference's merge; here
-//     its points are left out (bit 1).
+//   * a critical energy that is NaN (negative discriminant in add_inelastic_Eins, e.g. a positive Q far above a group
+//     edge): its points are left out (bit 1).  The reference ends there too -- every comparison of its merge fails on
+//     an all-NaN array, the whole other array is copied, and the one NaN its exit branch takes is cut off again
+//     (src/array_merge.F90:78-100; the oracle's literal merge shows it) -- so this bit is information, not a difference.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>

@@ -162,3 +162,42 @@ def test_device_sab_egrid_equals_the_oracle(mode, elastic):
             _same(got, pyoracle.sab_egrid(sab, eb, sab_epts_per_bin=epts), f"sab_egrid {mode} {elastic} SAB_EPTS_PER_BIN={epts}")
     finally:
         ds.clear()
+
+
+@pytest.mark.gpu
+def test_device_grid_status_word():
+    """The status word.  A NaN critical energy of add_inelastic_Eins (a reaction with positive Q at group edges far below
+    |Q|: negative discriminant, src/scatt.F90:489) leaves its points out and sets bit 1; the reference's merge drops an
+    all-NaN array too (every comparison fails, array_merge.F90:78-100), so device, numpy restatement and the oracle's
+    literal chain agree in every bit.  A value repeated inside an input array is dropped and sets bit 2."""
+    import copy
+    from ndpp_b200 import scatt
+    name, nuc, eb, params = NUCLIDES[0]
+    nuc2 = copy.deepcopy(nuc)
+    lvl = [r for r in nuc2.reactions if 51 <= r.MT <= 90][0]
+    lvl.Q_value = 0.75
+    dn = scatt.DeviceNuclide(nuc2, eb, params)
+    try:
+        d_el, d_inel, status = dn.create_ein_grid()
+    finally:
+        dn.clear()
+    assert status & 2
+    el, inel = egrid.create_Ein_grid(nuc2, eb)
+    _same(d_el, el, "positive Q: Ein_el")
+    _same(d_inel, inel, "positive Q: Ein_inel")
+    assert np.all(np.isfinite(d_inel))
+    rn = pyoracle.RefNuclide(nuc2, eb, params)
+    try:
+        r_el, r_inel = rn.create_ein_grid()
+    finally:
+        rn.close()
+    _same(d_el, r_el, "positive Q: Ein_el vs the oracle")
+    _same(d_inel, r_inel, "positive Q: Ein_inel vs the oracle")
+    eb2 = np.concatenate([eb[:5], eb[4:]])          # one edge twice
+    dn = scatt.DeviceNuclide(nuc, eb2, params)
+    try:
+        d_el, d_inel, status = dn.create_ein_grid()
+    finally:
+        dn.clear()
+    assert status & 4
+    assert np.all(np.diff(d_el) > 0) and np.all(np.diff(d_inel) > 0)

@@ -152,6 +152,31 @@ def test_cpp_driver_writes_the_library_the_python_driver_writes(tool, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cpp_driver_builds_the_ein_grids_on_the_device(tool, tmp_path):
+    """--ein-grid: the per-nuclide body of preprocess_ndpp including create_Ein_grid (src/scatt.F90:139) from the C++ host
+    layer (ScattDataSet::create_Ein_grid) against the Python driver with no grids given: identical library files, and the
+    grid in the file is the oracle's."""
+    from ndpp_b200 import driver, output
+    from oracle import pyoracle
+    nuc = small_heavy()
+    nuc.name = "92238.71c"
+    e_bins = synth.group_structure(70)
+    params = ace.Params(order=3, mu_bins=501, nuscatter=False)
+    dump.write_nuclide_case(tmp_path / "g.case", nuc, e_bins, params.scatt_type, params.order, params.mu_bins, False,
+                            np.array([1.0]), np.array([1.0]), params)
+    cpp, py = tmp_path / "cpp.bin", tmp_path / "py.bin"
+    r = subprocess.run([tool, str(tmp_path / "g.case"), str(tmp_path / "g.res"), "--library", str(cpp), "--name", nuc.name,
+                        "--print-tol", "1e-8", "--thin-tol", "0", "--ein-grid"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    res = driver.preprocess_nuclide(nuc, e_bins, params, print_tol=1e-8, thin_tol=0.0, library_file=str(py))
+    assert open(cpp, "rb").read() == open(py, "rb").read()
+    rn = pyoracle.RefNuclide(nuc, e_bins, params)
+    el, inel = rn.create_ein_grid()
+    rn.close()
+    assert np.array_equal(res.Ein_el, el) and np.array_equal(res.Ein_inel, inel)
+
+
+@pytest.mark.gpu
 def test_cpp_calc_scatt_c1(tool, oracle, tmp_path):
     from ndpp_b200 import scatt
     nuc, e_bins, params = synth.c1_fixture()

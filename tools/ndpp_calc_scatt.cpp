@@ -7,6 +7,8 @@
 //                                                               nuclide together (ndppgpu_group_*, nuclide cases)
 //                   [--library FILE [--ascii] [--name ZAID] [--print-tol P] [--thin-tol T]]   nuclide cases only
 //                   [--library-only]
+//   --ein-grid (with --library, one device): the E_in grids are built by create_Ein_grid on the device
+//   (ndppgpu_nuclide_create_ein_grid) instead of being read from the case file
 //
 // With --library the program does what the per-nuclide body of preprocess_ndpp does (src/ndpp.F90:560-702):
 // calc_scatt, apply_tol_scatt and thin_grid in one device call per matrix set (ndppgpu_*_thinned), then init_library
@@ -100,7 +102,7 @@ void write_result(const char* path, double kind, int G, int L, const std::vector
 struct Options {
     int device = -1, devices = -1;
     std::string library, name = "synthetic";
-    bool ascii = false, library_only = false;
+    bool ascii = false, library_only = false, ein_grid = false;
     double print_tol = 1.0e-8, thin_tol = 0.0;   // print_tol default of src/constants.F90; thin_tol as a fraction
 };
 
@@ -174,6 +176,8 @@ void run_nuclide(const Context* ctx, const DeviceGroup* group, Reader& r, const 
         std::unique_ptr<ScattDataSet> set(group ? new ScattDataSet(*group, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st)
                                                 : new ScattDataSet(*ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st));
         ScattDataSet& rxn_data = *set;
+        // create_Ein_grid (src/scatt.F90:139) on the device instead of the grids of the case file
+        if (opt.ein_grid) rxn_data.create_Ein_grid(xe, xi);
         rxn_data.calc_elastic_thinned(xe, opt.print_tol, opt.thin_tol, energy_bins, el_mat, compr, err);
         if (!xi.empty())
             rxn_data.calc_inelastic_thinned(xi, nuscatt, opt.print_tol, opt.thin_tol, energy_bins, inel_mat, nuinel_mat,
@@ -228,7 +232,7 @@ int main(int argc, char** argv)
 {
     try {
         const char* usage = "usage: ndpp_calc_scatt CASE RESULT [--device N | --devices N] [--library FILE [--ascii] [--name ZAID] "
-                            "[--print-tol P] [--thin-tol T]] [--library-only]";
+                            "[--print-tol P] [--thin-tol T] [--ein-grid]] [--library-only]";
         if (argc < 3) fatal_error(usage);
         Options opt;
         for (int i = 3; i < argc; ++i) {
@@ -242,6 +246,7 @@ int main(int argc, char** argv)
             else if (a == "--thin-tol") opt.thin_tol = std::atof(value());
             else if (a == "--ascii") opt.ascii = true;
             else if (a == "--library-only") opt.library_only = true;
+            else if (a == "--ein-grid") opt.ein_grid = true;
             else fatal_error(usage);
         }
         if (opt.library_only && opt.library.empty()) fatal_error(usage);
