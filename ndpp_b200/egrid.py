@@ -1,15 +1,16 @@
-"""Host-side incoming-energy grid builders: what stays on the reference's side of the seam.
+"""Incoming-energy grid builders, host restatement (numpy).
 
 In the reference these routines run in Fortran *before* the hot path and hand it the E_in grids:
   merge               src/array_merge.F90:13-107
   create_Ein_grid     src/scatt.F90:166-236   (combine_Eins :246, add_elastic_Eins :311,
                       add_one_more_point :426, add_inelastic_Eins :456)
   sab_egrid           src/sab.F90:460-568
-They are restated here (numpy, host) only so that the benchmark configurations can be driven with
-the same kind of grids the reference builds; the grids are *inputs* of both the CUDA path and the
-oracle, so nothing here influences parity.  One simplification: `merge` is implemented as a sorted
-union, which equals the reference's two-pointer merge whenever neither input holds repeated values
-(the reference keeps repeats that occur inside one array).
+The product builds them on the device (csrc/kernels_egrid.cuh: DeviceNuclide.create_ein_grid, DeviceSab.egrid).  This
+module is the independent statement of the same text that holds the oracle's literal chain of merges
+(oracle/egrid_ref.c) and the device path, bit for bit, in tests/test_egrid.py; the synthetic benchmark workloads
+(synth.py) and chi.py / output.py use its `merge` and `binary_search` for host-side bookkeeping.  `merge` is a sorted
+union, which equals the reference's two-pointer merge whenever neither input holds repeated values (the reference
+keeps some repeats that occur inside one array); log and exp are the C library's, as the gfortran build calls them.
 """
 from __future__ import annotations
 
