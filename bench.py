@@ -434,6 +434,7 @@ def run_b200(args):
             cgroup.close()
         else:
             gn.clear()
+            extra["configs"] = run_configs_group(group, ctx, peak, dist, dev)
             extra["c5_library"] = library.run_c5(group, args.c5_nuclides, dist=dist, device=dev)
         if breakdown:
             extra["strong_scaling_breakdown"] = breakdown
@@ -496,6 +497,69 @@ def _cpu_rate_nuclide(nuc, e_bins, params, Ein_el, Ein_inel, n, threads, counter
     cnt = pyoracle.freegas_counters(reset=True) if counters else None
     rn.close()
     return ev / dt, len(pick(Ein_el)), cnt
+
+
+def run_configs_group(group, ctx, peak_tflops, dist, dev):
+    """The nuclide configurations other than the headline one on the device group (N > 1): C1 and C3 at three
+    temperatures through ndppgpu_group_* -- the E_in grid dealt cyclically over the GPUs, the columns gathered to the
+    root -- second pass of each.  evals/s from the host clock around integrate + sync (max over ranks: kernels, gather
+    and assembly inside), kernel ms = the slowest rank's CUDA-event time, roofline against N times the measured peak.
+    (C4, S(a,b), has no sharded form: 5e4 E_in take 2 ms on one GPU; it is in the N = 1 line.)"""
+    import torch
+    from ndpp_b200 import synth
+    from ndpp_b200.group import GroupNuclide
+    world = dist.get_world_size()
+
+    def allred(x, op):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    rows = []
+
+    def row(name, nuc, e_bins, params, Eel, Einel, flops=None, freegas=False):
+        gn = GroupNuclide(nuc, e_bins, params, group)
+        gn.set_grids(Eel, Einel)
+        what = 1 | (2 if Einel is not None else 0)
+        for _ in range(2):
+            torch.cuda.synchronize()
+            dist.barrier()
+            ctx.stats(reset=True)
+            t0 = time.perf_counter()
+            gn.integrate(what)
+            gn.sync()
+            wall = time.perf_counter() - t0
+        st = ctx.stats(reset=True)
+        gn.clear()
+        wall = allred(wall, dist.ReduceOp.MAX)
+        kms = allred(st["kernel_ms"], dist.ReduceOp.MAX)
+        G, L = len(e_bins) - 1, params.order + 1
+        ev = (len(Eel) + (len(Einel) if Einel is not None else 0)) * G * L
+        r = {"config": name, "n_gpus": world, "evals": int(ev), "evals_per_s": ev / wall, "ms": wall * 1e3,
+             "kernel_ms_slowest_rank": kms, "evals_per_s_kernel": ev / (kms * 1e-3)}
+        if freegas:
+            nk = allred(st["freegas_kernel_evals"], dist.ReduceOp.SUM)
+            ns = allred(st["freegas_sab_evals"], dist.ReduceOp.SUM)
+            flops = 40.0 * nk + 35.0 * ns
+            r["kernel_evals"] = int(nk)
+        if flops:
+            ach = flops / (kms * 1e-3) / 1e12
+            r["roofline"] = {"bound": "fp64", "algorithmic_flops": flops, "achieved": ach, "peak": peak_tflops * world,
+                             "unit": "TFLOP/s", "frac": ach / (peak_tflops * world),
+                             "formula": "as extra.configs of the N = 1 line; peak = N x the measured FP64 peak"}
+        rows.append(r)
+
+    nuc, e_bins, params = synth.c1_fixture()
+    Ein = synth.c1_ein_grid(997)
+    G, L, M = len(e_bins) - 1, params.order + 1, params.mu_bins
+    FA = 12 + 22 * G + 40 * 2 + (M + 2) * (13 + 4 * (L - 2) + 10 * L)
+    FC = 2 * M * (13 + 2 * G) + G * (M - 1) * (15 * L + 11)
+    row("C1 tests/test_scatt fixture (MT 51/52 relabelled), 1000 E_in", nuc, e_bins, params, Ein, Ein,
+        flops=float(len(Ein) * (2 * FA + 2 * FA + FC)))
+    for kT, T in ((synth.KT_293K, 293.6), (synth.KT_600K, 600), (synth.KT_1200K, 1200)):
+        nuc, e_bins, params, Ein = synth.c3_h1_freegas(kT=kT)
+        row(f"C3 H-1 free gas {T} K, P3, 70 groups, 1000 E_in", nuc, e_bins, params, Ein, None, freegas=True)
+    return rows
 
 
 def run_ein_grid(ctx, nuc, e_bins, params, sample_cpu=True):
