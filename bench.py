@@ -357,10 +357,10 @@ def run_b200(args):
     if world == 1:
         def step_e2e():
             dn2 = scatt.DeviceNuclide(nuc, e_bins, params, ctx)
-            dn2.elastic(h_Eel, out=h_el)
-            dn2.inelastic(h_Ein, False, out=h_inel)
+            dn2.calc(h_Eel, h_Ein, False, el_out=h_el, inel_out=h_inel)
             dn2.clear()
-        e2e_call = "ndpp_b200.scatt.DeviceNuclide(...) + elastic(host) + inelastic(host) == calc_scatt"
+        e2e_call = ("ndpp_b200.scatt.DeviceNuclide(...) + calc(host grids, host matrices) == calc_scatt (ndppgpu_calc_scatt: "
+                    "the elastic matrices leave for the host while the inelastic kernels run)")
     else:
         def step_e2e():   # table upload + convert_distro on every GPU, deal of the grids, integration, NCCL gather, D2H on the root
             g2 = GroupNuclide(nuc, e_bins, params, group)

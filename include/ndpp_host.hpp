@@ -258,6 +258,25 @@ public:
         ctx_.check(group_ ? ndppgpu_group_elastic(h_, Ein.data(), (int)Ein.size(), el_mat.data())
                           : ndppgpu_elastic(h_, Ein.data(), (int)Ein.size(), el_mat.data()));
     }
+    // both grids in one call (src/scatt.F90:143-150): the elastic matrices are copied to the host while the inelastic
+    // kernels run (ndppgpu_calc_scatt); on a device group the two calls above
+    void calc_grids(const std::vector<double>& Ein_el, const std::vector<double>& Ein_inel, bool nuscatt,
+                    std::vector<double>& el_mat, std::vector<double>& inel_mat, std::vector<double>& nuinel_mat) const
+    {
+        if (group_) {
+            calc_elastic_grid(Ein_el, el_mat);
+            inel_mat.clear(); nuinel_mat.clear();
+            if (!Ein_inel.empty()) calc_inelastic_grid(Ein_inel, nuscatt, inel_mat, nuinel_mat);
+            return;
+        }
+        const size_t w = (size_t)groups_ * order_;
+        el_mat.assign(Ein_el.size() * w, 0.0);
+        inel_mat.assign(Ein_inel.size() * w, 0.0);
+        if (nuscatt && !Ein_inel.empty()) nuinel_mat.assign(inel_mat.size(), 0.0); else nuinel_mat.clear();
+        auto out = [](std::vector<double>& v) { return v.empty() ? nullptr : v.data(); };
+        ctx_.check(ndppgpu_calc_scatt(h_, detail::ptr_or_null(Ein_el), (int)Ein_el.size(), out(el_mat),
+                                      detail::ptr_or_null(Ein_inel), (int)Ein_inel.size(), out(inel_mat), out(nuinel_mat)));
+    }
     // calc_inelastic_grid (src/scatt.F90:682-778); nuinel_mat stays empty unless nuscatt
     void calc_inelastic_grid(const std::vector<double>& Ein, bool nuscatt, std::vector<double>& inel_mat,
                              std::vector<double>& nuinel_mat) const
@@ -381,10 +400,7 @@ inline void calc_scatt(const Context& ctx, const Nuclide& nuc, const std::vector
                        std::vector<double>& nuinel_mat, const Settings& st = Settings())
 {
     ScattDataSet rxn_data(ctx, nuc, energy_bins, scatt_type, order, mu_bins, nuscatt, st);
-    rxn_data.calc_elastic_grid(Ein_el, el_mat);
-    inel_mat.clear();
-    nuinel_mat.clear();
-    if (!Ein_inel.empty()) rxn_data.calc_inelastic_grid(Ein_inel, nuscatt, inel_mat, nuinel_mat);
+    rxn_data.calc_grids(Ein_el, Ein_inel, nuscatt, el_mat, inel_mat, nuinel_mat);
     rxn_data.clear();
 }
 

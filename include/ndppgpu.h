@@ -125,6 +125,11 @@ int ndppgpu_nuclide_get_table(void *nuc, int slot, int iE, double *distro, doubl
  * keep convert_distro on the host (its tables then are bit-identical to the reference's own libm),
  * and lets the parity tests separate the integrators from the table conversion. */
 int ndppgpu_nuclide_set_table(void *nuc, int slot, int iE, const double *distro);
+/* ndppgpu_elastic + ndppgpu_inelastic as calc_scatt calls them one after the other (src/scatt.F90:143-150), in one call:
+ * the elastic matrices are copied to the host while the inelastic kernels run.  Either grid may be empty (NE 0, null
+ * pointers); nuinel_mat may be null.  Same results as the two calls. */
+int ndppgpu_calc_scatt(void *nuc, const double *Ein_el, int NE_el, double *el_mat, const double *Ein_inel, int NE_inel,
+                       double *inel_mat, double *nuinel_mat);
 /* ScattData%interp_distro (src/scattdata_header.F90:391-499) of one slot at NE incoming energies:
  * distro[NE][G][L], scaled by sigma_s * p_valid for non-elastic reactions exactly as the reference. */
 int ndppgpu_interp_distro(void *nuc, int slot, const double *Ein, int NE, double *distro);

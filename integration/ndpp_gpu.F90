@@ -27,6 +27,7 @@ module ndpp_gpu
   public :: ndppgpu_init, ndppgpu_finalize, ndppgpu_last_error
   public :: ndppgpu_nuclide_create, ndppgpu_nuclide_add_reaction, ndppgpu_convert_distro
   public :: ndppgpu_elastic, ndppgpu_inelastic, ndppgpu_nuclide_free
+  public :: ndppgpu_calc_scatt
   public :: ndppgpu_nuclide_create_ein_grid, ndppgpu_nuclide_ein_grid, ndppgpu_sab_egrid, ndppgpu_sab_ein_grid
   public :: ndppgpu_elastic_thinned, ndppgpu_inelastic_thinned
   public :: ndppgpu_apply_tol, ndppgpu_thin_grid
@@ -184,6 +185,18 @@ module ndpp_gpu
       real(c_double), intent(out)   :: compression, max_abs_err
       integer(c_int)                :: rc
     end function ndppgpu_inelastic_thinned
+
+    ! ndppgpu_elastic + ndppgpu_inelastic in one call (src/scatt.F90:143-150): el_mat leaves for the host while the
+    ! inelastic kernels run; nuinel_mat = c_null_ptr when nuscatt is .false.
+    function ndppgpu_calc_scatt(nuc, Ein_el, NE_el, el_mat, Ein_inel, NE_inel, inel_mat, nuinel_mat) &
+         bind(C, name="ndppgpu_calc_scatt") result(rc)
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value          :: nuc, nuinel_mat
+      integer(c_int), value       :: NE_el, NE_inel
+      real(c_double), intent(in)  :: Ein_el(*), Ein_inel(*)
+      real(c_double), intent(out) :: el_mat(*), inel_mat(*)
+      integer(c_int)              :: rc
+    end function ndppgpu_calc_scatt
 
     ! create_Ein_grid (src/scatt.F90:166-236) on the device; lengths back, then ndppgpu_nuclide_ein_grid copies a grid
     function ndppgpu_nuclide_create_ein_grid(nuc, extend_pts, inel_extend_pts, n_el, n_inel, status) &

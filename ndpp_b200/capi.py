@@ -27,7 +27,7 @@ EXPORTS = ["ndppgpu_init", "ndppgpu_finalize", "ndppgpu_last_error", "ndppgpu_st
            "ndppgpu_test_exact_math", "ndppgpu_apply_tol", "ndppgpu_apply_tol_dev", "ndppgpu_thin_grid",
            "ndppgpu_thin_grid_dev", "ndppgpu_gather_columns_dev", "ndppgpu_elastic_thinned",
            "ndppgpu_inelastic_thinned", "ndppgpu_chi", "ndppgpu_eval_libm",
-           "ndppgpu_nuclide_create_ein_grid", "ndppgpu_nuclide_ein_grid", "ndppgpu_sab_egrid", "ndppgpu_sab_ein_grid",
+           "ndppgpu_calc_scatt", "ndppgpu_nuclide_create_ein_grid", "ndppgpu_nuclide_ein_grid", "ndppgpu_sab_egrid", "ndppgpu_sab_ein_grid",
            "ndppgpu_group_init", "ndppgpu_group_unique_id", "ndppgpu_group_init_rank", "ndppgpu_group_info",
            "ndppgpu_group_ctx", "ndppgpu_group_gathered_bytes", "ndppgpu_group_finalize",
            "ndppgpu_group_nuclide_create", "ndppgpu_group_nuclide_add_reaction", "ndppgpu_group_convert_distro",
@@ -104,6 +104,7 @@ def load() -> C.CDLL:
     L.ndppgpu_convert_distro.argtypes = [vp]
     L.ndppgpu_elastic.argtypes = [vp, c_dp, i, c_dp]
     L.ndppgpu_inelastic.argtypes = [vp, c_dp, i, c_dp, c_dp]
+    L.ndppgpu_calc_scatt.argtypes = [vp, c_dp, i, c_dp, c_dp, i, c_dp, c_dp]
     L.ndppgpu_elastic_dev.argtypes = [vp, vp, i, vp]
     L.ndppgpu_inelastic_dev.argtypes = [vp, vp, i, vp, vp]
     L.ndppgpu_nuclide_n_slots.argtypes = [vp]

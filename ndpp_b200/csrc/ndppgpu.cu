@@ -38,6 +38,7 @@ thread_local std::string g_last_error;  // context-less failures (ndppgpu_init),
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // ndppgpu_calc_scatt: the elastic matrices leave while the inelastic kernels run
     std::string err;
     ndppgpu_stats_t stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_all, pending_f6;
@@ -1241,6 +1242,7 @@ int ndppgpu_init(int device, void** ctx)
     c->device = device;
     CK(nullptr, cudaSetDevice(device));
     CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(nullptr, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     {
         const char* e = std::getenv("NDPPGPU_F6_LEGACY");
@@ -1274,6 +1276,7 @@ int ndppgpu_finalize(void* ctx)
     for (auto& p : c->pending_f6) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (void* p : {c->f6_rec, c->f6_sorted, c->f6_femu, c->f6_part}) if (p) cudaFree(p);
     cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     return 0;
 }
@@ -1563,6 +1566,52 @@ int ndppgpu_inelastic(void* nuc, const double* Ein, int NE, double* inel_mat, do
     if (nuinel_mat) CK(c, cudaMemcpyAsync(nuinel_mat, d_nu.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (double)(nout * sizeof(double) * (nuinel_mat ? 2 : 1));
+    return 0;
+}
+
+// calc_elastic_grid + calc_inelastic_grid as calc_scatt calls them one after the other (src/scatt.F90:143-150), in one
+// call: the elastic matrices are copied to the host on a second stream while the inelastic kernels run.
+int ndppgpu_calc_scatt(void* nuc, const double* Ein_el, int NE_el, double* el_mat, const double* Ein_inel, int NE_inel,
+                       double* inel_mat, double* nuinel_mat)
+{
+    Nuclide* n = (Nuclide*)nuc;
+    if (!n) return fail(nullptr, "ndppgpu_calc_scatt: null argument");
+    Ctx* c = n->ctx;
+    if ((NE_el > 0 && (!Ein_el || !el_mat)) || (NE_inel > 0 && (!Ein_inel || !inel_mat)))
+        return fail(c, "ndppgpu_calc_scatt: null argument");
+    CK(c, cudaSetDevice(c->device));
+    const size_t w = (size_t)n->G * n->L;
+    TmpBuf d_Eel, d_el, d_Ein, d_inel, d_nu;
+    cudaEvent_t ev = nullptr;
+    if (NE_el > 0) {
+        if (tmp_upload(c, d_Eel, Ein_el, (size_t)NE_el) || tmp_alloc(c, d_el, NE_el * w * sizeof(double))) return 1;
+        if (elastic_dev(n, d_Eel.as<double>(), NE_el, d_el.as<double>())) return 1;
+        CK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(c, cudaEventRecord(ev, c->stream));
+    }
+    int rc = 0;
+    if (NE_inel > 0) {
+        rc = tmp_upload(c, d_Ein, Ein_inel, (size_t)NE_inel) || tmp_alloc(c, d_inel, NE_inel * w * sizeof(double)) ||
+             (nuinel_mat && tmp_alloc(c, d_nu, NE_inel * w * sizeof(double)));
+        if (!rc) rc = inelastic_dev(n, d_Ein.as<double>(), NE_inel, d_inel.as<double>(), nuinel_mat ? d_nu.as<double>() : nullptr);
+    }
+    // the inelastic kernels are queued (or running): now the elastic result leaves on the copy stream
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (NE_el > 0) {
+        e1 = cudaStreamWaitEvent(c->copy_stream, ev, 0);
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(el_mat, d_el.p, NE_el * w * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream);
+    }
+    if (!rc && NE_inel > 0) {
+        e2 = cudaMemcpyAsync(inel_mat, d_inel.p, NE_inel * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e2 == cudaSuccess && nuinel_mat)
+            e2 = cudaMemcpyAsync(nuinel_mat, d_nu.p, NE_inel * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    }
+    const cudaError_t e3 = cudaStreamSynchronize(c->copy_stream), e4 = cudaStreamSynchronize(c->stream);
+    if (ev) cudaEventDestroy(ev);
+    if (rc) return 1;
+    for (cudaError_t e : {e1, e2, e3, e4})
+        if (e != cudaSuccess) return fail(c, std::string("ndppgpu_calc_scatt: ") + cudaGetErrorString(e));
+    c->stats.d2h_bytes += (double)((NE_el + (size_t)NE_inel * (nuinel_mat ? 2 : 1)) * w * sizeof(double));
     return 0;
 }
 

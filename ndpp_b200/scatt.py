@@ -126,6 +126,21 @@ class DeviceNuclide:
         check(self.lib.ndppgpu_inelastic(self.h, dp(Ein), len(Ein), dp(out), dp(nu)), self.ctx.h)
         return out, nu
 
+    def calc(self, Ein_el, Ein_inel=None, nuscatt=None, el_out=None, inel_out=None, nu_out=None):
+        """elastic + inelastic in one call (ndppgpu_calc_scatt): the elastic matrices are copied to the host while the
+        inelastic kernels run.  Returns (el, inel, nu); inel / nu are None without an inelastic grid."""
+        Eel = f64(Ein_el)
+        nuscatt = self.params.nuscatter if nuscatt is None else nuscatt
+        el = self._out(el_out, len(Eel))
+        Ein = inel = nu = None
+        if Ein_inel is not None and len(Ein_inel) > 0:
+            Ein = f64(Ein_inel)
+            inel = self._out(inel_out, len(Ein))
+            nu = self._out(nu_out, len(Ein)) if nuscatt else None
+        check(self.lib.ndppgpu_calc_scatt(self.h, dp(Eel), len(Eel), dp(el), dp(Ein), 0 if Ein is None else len(Ein),
+                                          dp(inel), dp(nu)), self.ctx.h)
+        return el, inel, nu
+
     # -- device-resident variants (torch CUDA tensors of dtype float64) --------------------------
     def elastic_dev(self, d_Ein, d_out):
         check(self.lib.ndppgpu_elastic_dev(self.h, d_Ein.data_ptr(), int(d_Ein.numel()), d_out.data_ptr()), self.ctx.h)
@@ -176,10 +191,7 @@ def calc_scatt(nuc: Nuclide, energy_bins, scatt_type: int, order: int, mu_bins: 
     p = Params(**{**p.__dict__, "scatt_type": scatt_type, "order": order, "mu_bins": mu_bins, "nuscatter": nuscatt})
     dn = DeviceNuclide(nuc, energy_bins, p, ctx)
     try:
-        el = dn.elastic(Ein_el)
-        inel = nu = None
-        if Ein_inel is not None and len(Ein_inel) > 0:
-            inel, nu = dn.inelastic(Ein_inel, nuscatt)
+        el, inel, nu = dn.calc(Ein_el, Ein_inel, nuscatt)
     finally:
         dn.clear()
     return el, inel, nu

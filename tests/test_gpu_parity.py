@@ -458,6 +458,29 @@ def test_freegas_work_items_do_not_change_the_bits(scatt, monkeypatch):
     assert items[0] < items[1] < items[2] < items[3] and items[4] == items[1]
 
 
+def test_calc_scatt_in_one_call_equals_the_two_calls(scatt):
+    """ndppgpu_calc_scatt (elastic + inelastic, the elastic matrices copied to the host while the inelastic kernels run)
+    against ndppgpu_elastic + ndppgpu_inelastic: the same bits, with and without nu-scatter, with and without an
+    inelastic grid, into caller-owned arrays."""
+    nuc, e_bins, params = synth.c1_fixture()
+    params = ace.Params(**{**params.__dict__, "nuscatter": True})
+    Ein = synth.c1_ein_grid(60)
+    Einel = Ein[Ein >= 2.0]
+    dn = scatt.DeviceNuclide(nuc, e_bins, params)
+    try:
+        el, (inel, nu) = dn.elastic(Ein), dn.inelastic(Einel, True)
+        a, b, c = dn.calc(Ein, Einel, True)
+        assert np.array_equal(a, el) and np.array_equal(b, inel) and np.array_equal(c, nu)
+        out_el, out_in = np.full_like(el, -1.0), np.full_like(inel, -1.0)
+        a, b, c = dn.calc(Ein, Einel, False, el_out=out_el, inel_out=out_in)
+        assert a is out_el and b is out_in and c is None
+        assert np.array_equal(out_el, el) and np.array_equal(out_in, inel)
+        a, b, c = dn.calc(Ein, None)
+        assert np.array_equal(a, el) and b is None and c is None
+    finally:
+        dn.clear()
+
+
 def test_freegas_chunked_walk_does_not_change_the_bits(scatt, monkeypatch):
     """The inner (mu) recursion is walked level by level, or 128 intervals of a level at a time with the forest below a
     chunk folded before the next chunk starts (NDPPGPU_FG_CHUNK; csrc/kernels_freegas.cuh: fg_warp_simpson_mu): same intervals,
