@@ -62,6 +62,22 @@ __global__ void k_eg_copy(const double* __restrict__ src, int n, EgOut o, int ze
     eg_append(o, v, zero_to_min);
 }
 
+// the same for several arrays in one launch: element t of the concatenation belongs to array k with
+// first[k] <= t < first[k + 1] (the nuclide grid, the group structure and one grid per reaction channel: ~45 arrays)
+struct EgSrc { const double* p; int first; int pad; };
+__global__ void k_eg_copy_many(const EgSrc* __restrict__ srcs, int n_src, int total, EgOut o, int zero_to_min)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int lo = 0, hi = n_src;              // srcs[n_src].first == total
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (srcs[mid].first <= t) lo = mid; else hi = mid; }
+    const int i = t - srcs[lo].first, n = srcs[lo + 1].first - srcs[lo].first;
+    const double* __restrict__ src = srcs[lo].p;
+    const double v = src[i];
+    if (i + 1 < n && src[i + 1] == v) atomicOr(o.status, EG_ST_REPEAT);
+    eg_append(o, v, zero_to_min);
+}
+
 // add_elastic_Eins (src/scatt.F90:311-419).  Thread t < (nb-1) * extend: the upscatter point i = t % extend - extend of
 // group t / extend (:343-376); thread (nb-1) * extend + g: the downscatter points of group g, in order until the first
 // one that is not below the group's top (:391-407).

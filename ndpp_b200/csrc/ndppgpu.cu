@@ -1115,10 +1115,20 @@ int create_ein_grid(Nuclide* n, int extend_pts, int inel_extend_pts, int* n_el, 
     cap += 2LL * (nb - 1) * extend_pts + 8;
     // a zero survives the chain of merges only when every merged array starts with zero and no extension point exists
     const int zero_to_min = !(all_zero && nb <= 2 && cutoff == 0.0);
+    TmpBuf d_desc;
     {
         EgWork w;
         if (eg_begin(c, w, cap)) return 1;
-        for (auto& r : srcs) if (eg_copy(c, w, r.d, r.n, zero_to_min)) return 1;
+        {   // every input array in one launch
+            std::vector<EgSrc> desc;
+            int first = 0;
+            for (auto& r : srcs) { if (r.n > 0) { desc.push_back({r.d, first, 0}); first += r.n; } }
+            const int n_src = (int)desc.size();
+            desc.push_back({nullptr, first, 0});
+            if (tmp_upload(c, d_desc, desc.data(), desc.size())) return 1;
+            k_eg_copy_many<<<blocks_for(first, 256), 256, 0, c->stream>>>(d_desc.as<EgSrc>(), n_src, first, w.out, zero_to_min);
+            if (launch_check(c, "k_eg_copy_many")) return 1;
+        }
         k_eg_elastic_pts<<<blocks_for((long long)(nb - 1) * (extend_pts + 1), 128), 128, 0, c->stream>>>(
             n->d_e_bins.as<double>(), nb, n->awr, n->kT, cutoff, extend_pts, w.out);
         if (launch_check(c, "k_eg_elastic_pts")) return 1;
