@@ -7,6 +7,8 @@ against each other, bit for bit:
   * ndpp_b200/egrid.py: written first and separately, every merge as a sorted union (numpy), math.log / math.exp;
   * the device path (csrc/kernels_egrid.cuh): one thread per candidate point, radix sort, compaction, lm::log_ / lm::exp_.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -70,6 +72,66 @@ def test_oracle_other_extension_counts():
     el2, inel2 = egrid.create_Ein_grid(nuc, eb, extend_pts=7, inel_extend_pts=4)
     _same(el, el2, "Ein_el")
     _same(inel, inel2, "Ein_inel")
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "egrid_vectors.npz")
+
+
+def _golden_inputs():
+    eb = synth.group_structure(70)
+    nuc, _, p7 = NUCLIDES[0][1], None, NUCLIDES[0][3]
+    nuc3, eb3, p3, _ = synth.c3_h1_freegas()
+    return eb, nuc, p7, nuc3, eb3, p3
+
+
+def test_oracle_reproduces_the_committed_grids():
+    """tests/golden/egrid_vectors.npz (scripts/make_egrid_golden.py: the numpy statement, committed) against the oracle's
+    literal chain of merges."""
+    g = np.load(GOLDEN)
+    eb, nuc, p7, nuc3, eb3, p3 = _golden_inputs()
+    rn = pyoracle.RefNuclide(nuc, eb, p7)
+    try:
+        el, inel = rn.create_ein_grid()
+        _same(el, g["heavy4_el"], "Ein_el"); _same(inel, g["heavy4_inel"], "Ein_inel")
+        el, inel = rn.create_ein_grid(extend_pts=7, inel_extend_pts=4)
+        _same(el, g["heavy4_el_7_4"], "Ein_el 7/4"); _same(inel, g["heavy4_inel_7_4"], "Ein_inel 7/4")
+    finally:
+        rn.close()
+    rn = pyoracle.RefNuclide(nuc3, eb3, p3)
+    try:
+        _same(rn.create_ein_grid()[0], g["h1_el"], "H-1 Ein_el")
+    finally:
+        rn.close()
+    _same(pyoracle.sab_egrid(synth.c4_sab(mode="skewed", elastic="coherent", n_ein=20, n_eout=12), eb), g["sab_skewed_coherent"], "sab skewed")
+    _same(pyoracle.sab_egrid(synth.c4_sab(mode="cont"), eb, sab_epts_per_bin=0), g["sab_cont_0"], "sab cont")
+
+
+@pytest.mark.gpu
+def test_device_reproduces_the_committed_grids():
+    """The CUDA path against the committed vectors directly (not through the restatement)."""
+    from ndpp_b200 import scatt
+    g = np.load(GOLDEN)
+    eb, nuc, p7, nuc3, eb3, p3 = _golden_inputs()
+    dn = scatt.DeviceNuclide(nuc, eb, p7)
+    try:
+        el, inel, _ = dn.create_ein_grid()
+        _same(el, g["heavy4_el"], "Ein_el"); _same(inel, g["heavy4_inel"], "Ein_inel")
+        el, inel, _ = dn.create_ein_grid(extend_pts=7, inel_extend_pts=4)
+        _same(el, g["heavy4_el_7_4"], "Ein_el 7/4"); _same(inel, g["heavy4_inel_7_4"], "Ein_inel 7/4")
+    finally:
+        dn.clear()
+    dn = scatt.DeviceNuclide(nuc3, eb3, p3)
+    try:
+        _same(dn.create_ein_grid()[0], g["h1_el"], "H-1 Ein_el")
+    finally:
+        dn.clear()
+    for key, sab, epts in (("sab_skewed_coherent", synth.c4_sab(mode="skewed", elastic="coherent", n_ein=20, n_eout=12), 10),
+                           ("sab_cont_0", synth.c4_sab(mode="cont"), 0)):
+        ds = scatt.DeviceSab(sab)
+        try:
+            _same(ds.egrid(eb, sab_epts_per_bin=epts)[0], g[key], key)
+        finally:
+            ds.clear()
 
 
 SAB_CASES = [(m, e) for m in ("skewed", "equal", "cont") for e in (None, "coherent", "incoherent")]
